@@ -1,0 +1,125 @@
+// Shared helpers for the pyprob_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#include "../../include/pyprob_b200.h"
+
+#define PPB_NUM_SMS 148  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+void ppb_set_error(const char* fmt, ...);
+
+#define PPB_CHECK_ARG(cond, msg)                               \
+  do {                                                         \
+    if (!(cond)) {                                             \
+      ppb_set_error("%s: %s", __func__, msg);                  \
+      return PPB_EINVAL;                                       \
+    }                                                          \
+  } while (0)
+
+#define PPB_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (call);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      ppb_set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+      return (int)_e;                                                               \
+    }                                                                               \
+  } while (0)
+
+#define PPB_LAUNCH_CHECK()                                                          \
+  do {                                                                              \
+    cudaError_t _e = cudaGetLastError();                                            \
+    if (_e != cudaSuccess) {                                                        \
+      ppb_set_error("%s:%d launch: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return (int)_e;                                                               \
+    }                                                                               \
+  } while (0)
+
+static inline int ppb_grid_for(int64_t n, int threads, int items_per_thread, int max_waves = 8) {
+  int64_t blocks = (n + (int64_t)threads * items_per_thread - 1) / ((int64_t)threads * items_per_thread);
+  if (blocks < 1) blocks = 1;
+  // cap at a multiple of the SM count; kernels are grid-stride
+  int64_t cap = (int64_t)PPB_NUM_SMS * max_waves;
+  if (blocks > cap) blocks = cap;
+  return (int)blocks;
+}
+
+// ---- math constants (fp32, written the way torch.distributions writes them) -------------------
+#define PPB_LOG_SQRT_2PI 0.9189385332046727f  // math.log(math.sqrt(2*math.pi))
+#define PPB_INV_SQRT2 0.7071067811865476f
+#define PPB_EPS32 1.1920928955078125e-07f     // torch.finfo(torch.float32).eps
+#define PPB_LOG_EPSILON (-18.420680743952367f) // pyprob/util.py:35 log(1e-8)
+
+__device__ __forceinline__ float ppb_normal_lp(float v, float mu, float sigma) {
+  // torch/distributions/normal.py log_prob: -((v-mu)^2)/(2 var) - log(scale) - log(sqrt(2 pi))
+  float var = sigma * sigma;
+  float d = v - mu;
+  return -(d * d) / (2.0f * var) - logf(sigma) - PPB_LOG_SQRT_2PI;
+}
+
+__device__ __forceinline__ float ppb_std_normal_cdf(float x) {
+  // torch Normal(0,1).cdf: 0.5 * (1 + erf(x / sqrt(2)))
+  return 0.5f * (1.0f + erff(x * PPB_INV_SQRT2));
+}
+
+__device__ __forceinline__ float ppb_clamp_prob(float p) {
+  // pyprob/util.py:393-395 clamp_probs
+  return fminf(fmaxf(p, PPB_EPS32), 1.0f - PPB_EPS32);
+}
+
+__device__ __forceinline__ float ppb_truncnormal_lp(float v, float mu, float sigma, float lo, float hi) {
+  // pyprob/distributions/truncated_normal.py:24-30, :40-45
+  float alpha = (lo - mu) / sigma;
+  float beta = (hi - mu) / sigma;
+  float Z = ppb_std_normal_cdf(beta) - ppb_std_normal_cdf(alpha);
+  float log_sz = logf(sigma * Z);
+  float z = (v - mu) / sigma;
+  float inside = (v >= lo && v <= hi) ? 0.0f : -INFINITY;  // log(lb*ub)
+  return inside + (-(z * z) / 2.0f - PPB_LOG_SQRT_2PI) - log_sz;
+}
+
+__device__ __forceinline__ float ppb_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double ppb_warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float ppb_warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- Philox4x32-10 (counter-based; D. E. Shaw Research "Random123" published algorithm) --------
+struct ppb_philox {
+  uint32_t c[4];
+};
+__device__ __forceinline__ ppb_philox ppb_philox4x32_10(uint64_t seed, uint64_t idx, uint64_t offset) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t c0 = (uint32_t)idx, c1 = (uint32_t)(idx >> 32), c2 = (uint32_t)offset, c3 = (uint32_t)(offset >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  ppb_philox out; out.c[0] = c0; out.c[1] = c1; out.c[2] = c2; out.c[3] = c3;
+  return out;
+}
+// uniform in [0,1): 24 random bits
+__device__ __forceinline__ float ppb_u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+// uniform in (0,1]: for logs
+__device__ __forceinline__ float ppb_u01_open0(uint32_t x) { return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ float ppb_std_normal_from(uint32_t a, uint32_t b) {
+  // Box-Muller
+  float u1 = ppb_u01_open0(a), u2 = ppb_u01(b);
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}

@@ -1,0 +1,30 @@
+// Library-wide plumbing: thread-local error string, version, device probe.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void ppb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" {
+
+const char* ppb_last_error(void) { return g_err; }
+
+int ppb_version(void) { return 100; }
+
+int ppb_device_arch(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return -1;
+  return p.major * 10 + p.minor;
+}
+
+}  // extern "C"

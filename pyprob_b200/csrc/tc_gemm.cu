@@ -1,0 +1,183 @@
+// Tensor-core building blocks: operand packing + a tcgen05 GEMM over packed images.
+//   C[M,N] = A[M,K] * B[N,K]^T (+bias) (relu), 3xTF32 (fp32-faithful) or single-pass TF32.
+// Warp roles (192 threads): warp 0 = bulk-TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> global).  One 128x128 output tile per CTA.
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace {
+
+using namespace tc;
+
+// ---- pack: row-major fp32 -> swizzled tile image(s) ------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack(const float* __restrict__ X, int64_t rows, int64_t K, int64_t ldx,
+                                               float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t KB = (K + kTileK - 1) / kTileK;
+  const int64_t RT = (rows + kTileRows - 1) / kTileRows;
+  const int64_t chunks = RT * kTileRows * KB * 8;  // 16-byte chunks in the padded image
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < chunks; q += (int64_t)gridDim.x * blockDim.x) {
+    int64_t c = q & 7, t = q >> 3;
+    int64_t row = t / KB, kb = t % KB;  // consecutive threads walk along K of one row: coalesced reads
+    int64_t k0 = kb * kTileK + c * 4;
+    float x[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = (row < rows && k0 + j < K) ? __ldg(X + row * ldx + k0 + j) : 0.0f;
+    float h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_tf32(x[j], h[j], l[j]);
+    int64_t off = packed_offset(row, k0, KB);
+    *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+    if (lo) *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// ---- GEMM --------------------------------------------------------------------------------------------
+constexpr int kStages = 3;
+constexpr int kGemmThreads = 192;
+constexpr int kBN = 128;
+struct __align__(1024) GemmSmem {
+  float a_hi[kStages][kTileFloats];
+  float a_lo[kStages][kTileFloats];
+  float b_hi[kStages][kTileFloats];
+  float b_lo[kStages][kTileFloats];
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t tmem_full;
+  uint32_t tmem_base;
+};
+
+template <bool X3>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+k_gemm_packed(const float* __restrict__ A_hi, const float* __restrict__ A_lo, const float* __restrict__ B_hi,
+              const float* __restrict__ B_lo, float* __restrict__ C, int M, int N, int K, int64_t ldc,
+              const float* __restrict__ bias, int relu) {
+  extern __shared__ uint8_t smem_raw[];
+  GemmSmem& sm = *reinterpret_cast<GemmSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KB = (K + kTileK - 1) / kTileK;
+  const int mt = blockIdx.y, nt = blockIdx.x;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+    mbar_init(&sm.tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kBN>(&sm.tmem_base);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t bytes = (X3 ? 4u : 2u) * kTileBytes;
+      for (int kb = 0; kb < KB; ++kb) {
+        int s = kb % kStages;
+        uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&sm.empty[s], ph ^ 1);
+        mbar_expect_tx(&sm.full[s], bytes);
+        int64_t ao = ((int64_t)mt * KB + kb) * kTileFloats, bo = ((int64_t)nt * KB + kb) * kTileFloats;
+        bulk_g2s(sm.a_hi[s], A_hi + ao, kTileBytes, &sm.full[s]);
+        bulk_g2s(sm.b_hi[s], B_hi + bo, kTileBytes, &sm.full[s]);
+        if (X3) {
+          bulk_g2s(sm.a_lo[s], A_lo + ao, kTileBytes, &sm.full[s]);
+          bulk_g2s(sm.b_lo[s], B_lo + bo, kTileBytes, &sm.full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_tf32(128, kBN);
+      for (int kb = 0; kb < KB; ++kb) {
+        int s = kb % kStages;
+        uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&sm.full[s], ph);
+        fence_after_sync();
+        uint64_t ah = smem_desc_sw128(smem_u32(sm.a_hi[s])), bh = smem_desc_sw128(smem_u32(sm.b_hi[s]));
+        uint64_t al = smem_desc_sw128(smem_u32(sm.a_lo[s])), bl = smem_desc_sw128(smem_u32(sm.b_lo[s]));
+#pragma unroll
+        for (int k = 0; k < kTileK / 8; ++k) {
+          uint64_t adv = (uint64_t)(k * 8 * 4 >> 4);  // 32 bytes per UMMA_K step, encoded >> 4
+          uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+          if (X3) {
+            mma_tf32(tmem, al + adv, bh + adv, idesc, first);
+            mma_tf32(tmem, ah + adv, bl + adv, idesc, 1u);
+            mma_tf32(tmem, ah + adv, bh + adv, idesc, 1u);
+          } else {
+            mma_tf32(tmem, ah + adv, bh + adv, idesc, first);
+          }
+        }
+        mma_commit(&sm.empty[s]);  // frees the stage once these MMAs have read it
+      }
+      mma_commit(&sm.tmem_full);
+    }
+  } else {
+    // epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
+    const int q = warp & 3;
+    mbar_wait(&sm.tmem_full, 0);
+    fence_after_sync();
+    const int row = mt * 128 + q * 32 + lane;
+#pragma unroll 1
+    for (int cb = 0; cb < kBN / 32; ++cb) {
+      float v[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + cb * 32, v);
+      int col0 = nt * kBN + cb * 32;
+      if (row < M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          int col = col0 + j;
+          if (col < N) {
+            float x = v[j] + (bias ? __ldg(bias + col) : 0.0f);
+            if (relu) x = fmaxf(x, 0.0f);
+            C[(int64_t)row * ldc + col] = x;
+          }
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after_sync();
+    tmem_dealloc<kBN>(tmem);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t ppb_packed_floats(int64_t rows, int64_t K) {
+  int64_t RT = (rows + tc::kTileRows - 1) / tc::kTileRows, KB = (K + tc::kTileK - 1) / tc::kTileK;
+  return RT * KB * tc::kTileFloats;
+}
+
+int ppb_pack_tf32(const float* X, int64_t rows, int64_t K, int64_t ldx, float* hi_out, float* lo_out, void* stream) {
+  PPB_CHECK_ARG(X && hi_out && rows > 0 && K > 0 && ldx >= K, "bad arguments");
+  int64_t chunks = ppb_packed_floats(rows, K) / 4;
+  k_pack<<<ppb_grid_for(chunks, 256, 1), 256, 0, (cudaStream_t)stream>>>(X, rows, K, ldx, hi_out, lo_out);
+  PPB_LAUNCH_CHECK();
+  return PPB_OK;
+}
+
+int ppb_gemm_packed(const float* A_hi, const float* A_lo, const float* B_hi, const float* B_lo, float* C, int64_t M,
+                    int64_t N, int64_t K, int64_t ldc, const float* bias, int relu, int precision, void* stream) {
+  PPB_CHECK_ARG(A_hi && B_hi && C && M > 0 && N > 0 && K > 0 && ldc >= N, "bad arguments");
+  PPB_CHECK_ARG(precision == PPB_PREC_TF32X3 || precision == PPB_PREC_TF32, "precision must be TF32X3 or TF32");
+  PPB_CHECK_ARG(precision == PPB_PREC_TF32 || (A_lo && B_lo), "3xTF32 needs the lo images");
+  dim3 grid((unsigned)((N + kBN - 1) / kBN), (unsigned)((M + 127) / 128));
+  size_t smem = sizeof(GemmSmem) + 1024;
+  if (precision == PPB_PREC_TF32X3) {
+    PPB_CUDA(cudaFuncSetAttribute(k_gemm_packed<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_gemm_packed<true><<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(A_hi, A_lo, B_hi, B_lo, C, (int)M, (int)N,
+                                                                            (int)K, ldc, bias, relu);
+  } else {
+    PPB_CUDA(cudaFuncSetAttribute(k_gemm_packed<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_gemm_packed<false><<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(A_hi, A_lo, B_hi, B_lo, C, (int)M, (int)N,
+                                                                             (int)K, ldc, bias, relu);
+  }
+  PPB_LAUNCH_CHECK();
+  return PPB_OK;
+}
+
+}  // extern "C"
