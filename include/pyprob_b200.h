@@ -190,32 +190,52 @@ int ppb_net_set_tables(ppb_net* net, const ppb_addr_desc* addrs_host, int32_t n_
 int ppb_net_destroy(ppb_net* net);
 
 /* Encoded trace minibatch = what pyprob/nn/dataset.py:21-37 (Batch) + the Python loops of
- * inference_network_lstm.py:146-182 compute, as index tensors.  Traces are ordered by sub-batch,
- * sub-batches by decreasing length T (stable); rows are time-major: row(t,i) = row_off[t] + i for
- * the n_active[t] traces whose length exceeds t.  All arrays are DEVICE pointers. */
+ * inference_network_lstm.py:146-182 compute, as index tensors ("address/index tensors bit-exact").
+ * Traces are ordered by sub-batch, sub-batches by decreasing length T (stable w.r.t. the reference's
+ * dict-insertion order); rows are time-major: row(t,i) = row_off[t] + i for the n_active[t] traces whose
+ * length exceeds t (always a prefix of the trace order).  A "step" is one (t, sub-batch) pair.
+ * The whole batch travels as ONE contiguous image (header + arrays, built by
+ * pyprob_b200.encoding.pack_batch) so it moves host->device in a single copy; ppb_batch is the decoded
+ * view: `_host` fields point into the host image (planning), the rest into the device copy. */
 typedef struct {
   int32_t n_traces;       /* B: batch.size                                                   */
   int32_t n_sub;          /* S: len(batch.sub_batches)                                       */
   int32_t t_max;          /* longest controlled length                                       */
   int32_t n_rows;         /* R = sum_s B_s*T_s                                               */
   int32_t n_steps;        /* sum_t (#sub-batches active at t)                                */
-  const int32_t* trace_sub;   /* [B]   sub-batch of trace i                                   */
-  const int32_t* row_off;     /* [t_max+1]                                                    */
-  const int32_t* step_off;    /* [t_max+1] prefix over t of #active sub-batches              */
-  const int32_t* step_addr;   /* [n_steps] address id at (t, s)                               */
-  const int32_t* row_step;    /* [R]   step index of each row                                 */
-  const float* values;        /* [R]   sampled value at (t,i) (category index as float)       */
-  const float* prior0;        /* [R]   prior mean | low                                       */
-  const float* prior1;        /* [R]   prior stddev | high                                    */
-  const float* obs;           /* [B, obs_in_total] flattened observed values                  */
-  /* rows grouped by address for the proposal heads */
-  int32_t n_head_tiles;
-  const int32_t* head_tile_addr;  /* [n_head_tiles]                                          */
-  const int32_t* head_tile_start; /* [n_head_tiles] offset into head_rows                    */
-  const int32_t* head_tile_count; /* [n_head_tiles] <= PPB_HEAD_TILE_ROWS                    */
-  const int32_t* head_rows;       /* [R] row ids, grouped by address                         */
+  int32_t n_groups;       /* distinct addresses present in the batch                         */
+  int32_t obs_in_total;   /* row width of obs                                                */
+  int32_t reserved_;
+  /* host planning arrays */
+  const int32_t* row_off_host;     /* [t_max+1]                                              */
+  const int32_t* group_addr_host;  /* [n_groups]   address id of each group                  */
+  const int32_t* group_start_host; /* [n_groups+1] offsets into head_rows                    */
+  /* device arrays */
+  const int32_t* trace_sub;      /* [B]   sub-batch of trace i                                */
+  const int32_t* step_addr;      /* [n_steps] address id at (t, s)                            */
+  const int32_t* step_prev_addr; /* [n_steps] address id at (t-1, s), -1 at t = 0            */
+  const int32_t* step_row0;      /* [n_steps] first row of the step                           */
+  const int32_t* step_nrows;     /* [n_steps] B_s                                             */
+  const int32_t* row_step;       /* [R]   step index of each row                              */
+  const int32_t* row_prev;       /* [R]   row of the same trace at t-1, -1 at t = 0          */
+  const float* values;           /* [R]   sampled value at (t,i) (category index as float)    */
+  const float* prior0;           /* [R]   prior mean | low                                    */
+  const float* prior1;           /* [R]   prior stddev | high                                 */
+  const float* obs;              /* [B, obs_in_total] flattened observed values               */
+  const int32_t* head_rows;      /* [R] row ids grouped by address                            */
 } ppb_batch;
-#define PPB_HEAD_TILE_ROWS 64
+
+/* Batch image header: int64[PPB_IMAGE_HEADER_WORDS]; word 0 = magic, 1..7 = the seven int32 fields
+ * above in order, 8 = total bytes, 9.. = byte offsets of the arrays in the order they are declared
+ * above (row_off, group_addr, group_start, trace_sub, step_addr, step_prev_addr, step_row0, step_nrows,
+ * row_step, row_prev, values, prior0, prior1, obs, head_rows).  Every array is 16-byte aligned. */
+#define PPB_IMAGE_MAGIC 0x5050423230304231LL
+#define PPB_IMAGE_HEADER_WORDS 32
+int ppb_batch_from_image(const void* image_host, const void* image_dev, int64_t image_bytes,
+                         ppb_batch* out);
+/* sizeof() of the ABI structs, for binding self-checks: 0 = ppb_net_desc, 1 = ppb_addr_desc,
+ * 2 = ppb_batch, 3 = ppb_ff_desc, 4 = ppb_linear_desc */
+int64_t ppb_sizeof(int which);
 
 /* precision of the tensor-core GEMMs: 0 = 3xTF32 split (fp32-faithful, parity mode, default),
  * 1 = single-pass TF32, 2 = fp32 SIMT everywhere (bring-up / cross-check). */
@@ -224,14 +244,14 @@ typedef struct {
 #define PPB_PREC_FP32_SIMT 2
 
 int64_t ppb_ic_workspace_bytes(const ppb_net* net, int32_t n_traces, int32_t n_rows, int32_t t_max,
-                               int32_t n_steps);
+                               int32_t n_steps, int32_t n_groups);
 /* loss = sum over rows of -log q(value | h_row) / n_traces  (inference_network_lstm.py:218-220);
  * -inf log-probs are replaced by log(1e-8) with zero gradient (:207-217, util.py:278-284).
  * status_out[0] = number of rows whose log-prob is NaN/+inf after the repair (reference returns
  * (False, 0) when that is non-zero).  row_lp_out (nullable) fp32[R] per-row log q. */
 int ppb_ic_loss_forward(ppb_net* net, const float* arena, const ppb_batch* batch_host_struct,
                         void* workspace, int64_t workspace_bytes, int precision, float* loss_out,
-                        int32_t* status_out, float* row_lp_out, void* stream);
+                        int32_t* status_out, float* row_lp_out, int want_grad, void* stream);
 /* grad_arena += d(loss*grad_scale)/d(arena); must follow ppb_ic_loss_forward on the same workspace. */
 int ppb_ic_loss_backward(ppb_net* net, const float* arena, float* grad_arena,
                          const ppb_batch* batch_host_struct, void* workspace, int64_t workspace_bytes,

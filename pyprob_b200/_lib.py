@@ -46,8 +46,10 @@ _SIGNATURES = {
     'ppb_net_create': [C.c_void_p, C.c_void_p],
     'ppb_net_set_tables': [C.c_void_p, C.c_void_p, c_i32, C.c_void_p, c_i32, c_i64],
     'ppb_net_destroy': [C.c_void_p],
-    'ppb_ic_workspace_bytes': [C.c_void_p, c_i32, c_i32, c_i32, c_i32],
-    'ppb_ic_loss_forward': [C.c_void_p, c_f, C.c_void_p, c_f, c_i64, c_int, c_f, c_f, c_f, c_f],
+    'ppb_ic_workspace_bytes': [C.c_void_p, c_i32, c_i32, c_i32, c_i32, c_i32],
+    'ppb_batch_from_image': [C.c_void_p, c_f, c_i64, C.c_void_p],
+    'ppb_sizeof': [c_int],
+    'ppb_ic_loss_forward': [C.c_void_p, c_f, C.c_void_p, c_f, c_i64, c_int, c_f, c_f, c_f, c_int, c_f],
     'ppb_ic_loss_backward': [C.c_void_p, c_f, c_f, C.c_void_p, c_f, c_i64, c_int, c_flt, c_f],
     'ppb_adam_step': [c_f, c_f, c_f, c_f, c_i64, c_flt, c_flt, c_flt, c_flt, c_flt, c_i64, c_flt, c_f],
     'ppb_ic_infer_step': [C.c_void_p, c_f, c_f, c_int, c_i32, c_f, c_i32, c_f, c_int, c_f, c_int, c_f, c_f, c_f,
@@ -64,10 +66,11 @@ _RESTYPES = {
     'ppb_ic_workspace_bytes': c_i64,
     'ppb_ic_infer_workspace_bytes': c_i64,
     'ppb_packed_floats': c_i64,
+    'ppb_sizeof': c_i64,
 }
 # entry points whose integer return value is data, not a status
 _VALUE_RETURNS = {'ppb_version', 'ppb_device_arch', 'ppb_weights_num_partials', 'ppb_ic_workspace_bytes',
-                  'ppb_ic_infer_workspace_bytes', 'ppb_packed_floats'}
+                  'ppb_ic_infer_workspace_bytes', 'ppb_packed_floats', 'ppb_sizeof'}
 
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES.keys()) + ['ppb_last_error'])
 

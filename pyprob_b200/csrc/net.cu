@@ -1,0 +1,1208 @@
+// Proposal network: observe embedding -> LSTM -> per-address heads -> NLL, forward and the
+// hand-differentiated backward, over an encoded trace minibatch (include/pyprob_b200.h section 4).
+// Replaces pyprob/nn/inference_network_lstm.py:136-220 (_loss) + autograd (inference_network.py:493).
+//
+// Algorithmic restructuring relative to the reference's per-(t,b) concatenation (:146-182): the LSTM
+// input GEMM x_t W_ih^T is split by the block structure of x_t = [obs_emb(b) | smp_emb(t,b) | step_emb(t,s)]:
+//   P_obs[b]    = obs_emb[b]  W_ih[:, :E]^T           once per trace          (GEMM, K = E)
+//   P_step[t,s] = step_emb    W_ih[:, E+S:]^T + b_ih + b_hh   once per (step, sub-batch) (GEMM, K = 2(td+ad))
+//   smp term    = sum_j smp_emb[t,b,j] W_ih[:, E+j]   S FMAs per gate element, fused in the cell kernel
+// which removes the T-fold recomputation of the observation block.
+#include <vector>
+#include <string.h>
+
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "heads.cuh"
+
+using gemm::Problem;
+
+struct ppb_net {
+  ppb_net_desc desc;
+  std::vector<ppb_addr_desc> addrs;
+  std::vector<int64_t> type_off;
+  ppb_addr_desc* d_addrs = nullptr;
+  int64_t* d_type_off = nullptr;
+  int64_t arena_floats = 0;
+  int I = 0;        // LSTM input width  E + S + 2 (td + ad)
+  int dh_pad = 4;   // max head hidden width, padded to 4
+  int out_pad = 4;  // max head output width, padded to 4
+  // pinned staging ring for problem lists
+  Problem* h_stage[2] = {nullptr, nullptr};
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+  size_t stage_cap = 0;
+  int stage_idx = 0;
+};
+
+namespace {
+
+inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------------
+// workspace carving
+// ---------------------------------------------------------------------------------------------------
+struct Ws {
+  // forward
+  float* obs_act[PPB_MAX_OBS][PPB_MAX_FF_LAYERS];
+  float* obs_cat; float* fin_act[PPB_MAX_FF_LAYERS]; float* obs_emb;
+  float* p_obs; float* emb_cat; float* p_step; float* w_smp_t; float* smp_emb;
+  float* gates; float* c; float* h; float* hid; float* out_raw; float* row_lp; float* d_out;
+  float* loss_acc;  // [0] = sum of -lp ; int status at [1]
+  // backward
+  float* d_hid; float* dh; float* dh_rec; float* dc; float* d_pobs; float* d_pstep; float* d_smp; float* d_embcat;
+  float* d_obs_emb; float* d_fin_act[PPB_MAX_FF_LAYERS]; float* d_obs_cat; float* d_obs_act[PPB_MAX_OBS][PPB_MAX_FF_LAYERS];
+  Problem* problems; // device problem list
+  int64_t max_problems;
+  int64_t total_bytes;
+};
+
+struct Dims {
+  int B, R, T, NS, G;
+};
+
+Ws carve(const ppb_net* net, Dims d, void* base) {
+  const ppb_net_desc& D = net->desc;
+  Ws w;
+  memset(&w, 0, sizeof(w));
+  char* p = (char*)base;
+  int64_t off = 0;
+  auto take = [&](int64_t floats) {
+    float* r = (float*)(p + off);
+    off += align_up(floats * 4, 256);
+    return r;
+  };
+  const int H = D.lstm_dim, E = D.obs_dim, S = D.sample_dim, C2 = 2 * (D.type_dim + D.addr_dim);
+  for (int j = 0; j < D.num_obs; ++j)
+    for (int l = 0; l + 1 < D.obs_ff[j].num_layers; ++l) w.obs_act[j][l] = take((int64_t)d.B * D.obs_ff[j].layers[l].out_dim);
+  w.obs_cat = take((int64_t)d.B * E);
+  for (int l = 0; l + 1 < D.obs_final.num_layers; ++l) w.fin_act[l] = take((int64_t)d.B * D.obs_final.layers[l].out_dim);
+  w.obs_emb = take((int64_t)d.B * E);
+  w.p_obs = take((int64_t)d.B * 4 * H);
+  w.emb_cat = take((int64_t)d.NS * C2);
+  w.p_step = take((int64_t)d.NS * 4 * H);
+  w.w_smp_t = take((int64_t)S * 4 * H);
+  w.smp_emb = take((int64_t)d.R * S);
+  w.gates = take((int64_t)d.R * 4 * H);
+  w.c = take((int64_t)d.R * H);
+  w.h = take((int64_t)d.R * H);
+  w.hid = take((int64_t)d.R * net->dh_pad);
+  w.out_raw = take((int64_t)d.R * net->out_pad);
+  w.row_lp = take(d.R);
+  w.d_out = take((int64_t)d.R * net->out_pad);
+  w.loss_acc = take(64);
+  w.d_hid = take((int64_t)d.R * net->dh_pad);
+  w.dh = take((int64_t)d.R * H);
+  w.dh_rec = take((int64_t)d.B * H);
+  w.dc = take((int64_t)d.B * H);
+  w.d_pobs = take((int64_t)d.B * 4 * H);
+  w.d_pstep = take((int64_t)d.NS * 4 * H);
+  w.d_smp = take((int64_t)d.R * S);
+  w.d_embcat = take((int64_t)d.NS * C2);
+  w.d_obs_emb = take((int64_t)d.B * E);
+  for (int l = 0; l + 1 < D.obs_final.num_layers; ++l) w.d_fin_act[l] = take((int64_t)d.B * D.obs_final.layers[l].out_dim);
+  w.d_obs_cat = take((int64_t)d.B * E);
+  for (int j = 0; j < D.num_obs; ++j)
+    for (int l = 0; l + 1 < D.obs_ff[j].num_layers; ++l) w.d_obs_act[j][l] = take((int64_t)d.B * D.obs_ff[j].layers[l].out_dim);
+  // dgates reuses `gates`?  No: backward needs the activations; keep a separate buffer.
+  w.max_problems = 64 + 4LL * PPB_MAX_OBS * PPB_MAX_FF_LAYERS + 8LL * d.G + 4LL * d.T;
+  w.problems = (Problem*)take(w.max_problems * (int64_t)(sizeof(Problem) / 4));
+  w.total_bytes = off;
+  return w;
+}
+
+// dgates lives after the carved region (largest buffer; only needed by backward)
+inline float* dgates_ptr(const Ws& w, void* base) { return (float*)((char*)base + w.total_bytes); }
+inline int64_t dgates_bytes(const ppb_net* net, Dims d) { return align_up((int64_t)d.R * 4 * net->desc.lstm_dim * 4, 256); }
+
+// ---------------------------------------------------------------------------------------------------
+// problem-list builder
+// ---------------------------------------------------------------------------------------------------
+struct Builder {
+  std::vector<Problem> probs;
+  std::vector<gemm::Phase> phases;
+  void begin() { gemm::Phase ph; ph.first = (int)probs.size(); phases.push_back(ph); }
+  void add(Problem p) {
+    gemm::Phase& ph = phases.back();
+    p.tiles_m = (p.M + gemm::BM - 1) / gemm::BM;
+    p.tiles_n = (p.N + gemm::BN - 1) / gemm::BN;
+    p.tile_start = ph.tiles;
+    if (p.M <= 0 || p.N <= 0) return;
+    ph.tiles += p.tiles_m * p.tiles_n;
+    ph.count += 1;
+    probs.push_back(p);
+  }
+};
+
+inline Problem P0() {
+  Problem p;
+  memset(&p, 0, sizeof(p));
+  p.alpha = 1.0f;
+  return p;
+}
+
+// Y[M, N] (ldy) = act(X[M,K] (ldx) W[N,K]^T (ldw) + b)
+inline Problem linear_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw, const float* b, float* Y,
+                          int64_t ldy, int M, int N, int K, int flags) {
+  Problem p = P0();
+  p.A = X; p.sam = ldx; p.sak = 1;
+  p.B = W; p.sbn = ldw; p.sbk = 1;
+  p.C = Y; p.ldc = ldy; p.bias = b;
+  p.M = M; p.N = N; p.K = K; p.flags = flags;
+  return p;
+}
+// dX[M,K] (lddx) = dY[M,N] (lddy) W[N,K] (ldw)
+inline Problem linear_dx(const float* dY, int64_t lddy, const float* W, int64_t ldw, float* dX, int64_t lddx, int M,
+                         int N, int K, int flags) {
+  Problem p = P0();
+  p.A = dY; p.sam = lddy; p.sak = 1;   // reduction index = n
+  p.B = W; p.sbn = 1; p.sbk = ldw;     // B(k_out, n) = W[n*ldw + k_out]
+  p.C = dX; p.ldc = lddx;
+  p.M = M; p.N = K; p.K = N; p.flags = flags;
+  return p;
+}
+// dW[N,K] (ldw) += dY[M,N]^T X[M,K]   (reduction over rows m)
+inline Problem linear_dw(const float* dY, int64_t lddy, const float* X, int64_t ldx, float* dW, int64_t ldw, int M,
+                         int N, int K) {
+  Problem p = P0();
+  p.A = dY; p.sam = 1; p.sak = lddy;   // A(n_out, m) = dY[m*lddy + n_out]
+  p.B = X; p.sbn = 1; p.sbk = ldx;     // B(k_in, m)  = X[m*ldx + k_in]
+  p.C = dW; p.ldc = ldw;
+  p.M = N; p.N = K; p.K = M; p.flags = gemm::kAccumulate;
+  return p;
+}
+
+// observe-embedding forward phases (inference_network.py:132-139); one phase per depth level of the
+// per-observable FFs, then one per layer of the final FF
+void add_obs_embed(Builder& bl, const ppb_net_desc& D, const float* arena, const float* obs, int B,
+                   float* const (*obs_act)[PPB_MAX_FF_LAYERS], float* obs_cat, float* const* fin_act, float* obs_emb) {
+  const int E = D.obs_dim;
+  int max_depth = 0;
+  for (int j = 0; j < D.num_obs; ++j) max_depth = D.obs_ff[j].num_layers > max_depth ? D.obs_ff[j].num_layers : max_depth;
+  std::vector<int> in_off(D.num_obs), out_off(D.num_obs);
+  { int ci = 0, co = 0; for (int j = 0; j < D.num_obs; ++j) { in_off[j] = ci; out_off[j] = co; ci += D.obs_ff[j].in_dim; co += D.obs_ff[j].out_dim; } }
+  for (int l = 0; l < max_depth; ++l) {
+    bl.begin();
+    for (int j = 0; j < D.num_obs; ++j) {
+      const ppb_ff_desc& ff = D.obs_ff[j];
+      if (l >= ff.num_layers) continue;
+      const ppb_linear_desc& L = ff.layers[l];
+      const float* X = l == 0 ? obs + in_off[j] : obs_act[j][l - 1];
+      int64_t ldx = l == 0 ? D.obs_in_total : ff.layers[l - 1].out_dim;
+      bool last = (l == ff.num_layers - 1);
+      float* Y = last ? obs_cat + out_off[j] : obs_act[j][l];
+      int64_t ldy = last ? E : L.out_dim;
+      bl.add(linear_fwd(X, ldx, arena + L.w_off, L.in_dim, arena + L.b_off, Y, ldy, B, L.out_dim, L.in_dim, gemm::kRelu));
+    }
+  }
+  for (int l = 0; l < D.obs_final.num_layers; ++l) {
+    bl.begin();
+    const ppb_linear_desc& L = D.obs_final.layers[l];
+    const float* X = l == 0 ? obs_cat : fin_act[l - 1];
+    bool last = (l == D.obs_final.num_layers - 1);
+    float* Y = last ? obs_emb : fin_act[l];
+    bl.add(linear_fwd(X, L.in_dim, arena + L.w_off, L.in_dim, arena + L.b_off, Y, L.out_dim, B, L.out_dim, L.in_dim, gemm::kRelu));
+  }
+}
+
+int upload_and_get(ppb_net* net, const Builder& b, Problem* dev, int64_t cap, cudaStream_t st) {
+  size_t n = b.probs.size();
+  if ((int64_t)n > cap) { ppb_set_error("problem list overflow (%zu > %lld)", n, (long long)cap); return PPB_ENOMEM; }
+  if (n == 0) return PPB_OK;
+  if (net->stage_cap < n) {
+    for (int i = 0; i < 2; ++i) {
+      if (net->h_stage[i]) cudaFreeHost(net->h_stage[i]);
+      PPB_CUDA(cudaMallocHost((void**)&net->h_stage[i], n * 2 * sizeof(Problem)));
+      if (!net->ev_stage[i]) PPB_CUDA(cudaEventCreateWithFlags(&net->ev_stage[i], cudaEventDisableTiming));
+    }
+    net->stage_cap = n * 2;
+  }
+  int i = net->stage_idx;
+  net->stage_idx ^= 1;
+  PPB_CUDA(cudaEventSynchronize(net->ev_stage[i]));
+  memcpy(net->h_stage[i], b.probs.data(), n * sizeof(Problem));
+  PPB_CUDA(cudaMemcpyAsync(dev, net->h_stage[i], n * sizeof(Problem), cudaMemcpyHostToDevice, st));
+  PPB_CUDA(cudaEventRecord(net->ev_stage[i], st));
+  return PPB_OK;
+}
+
+int run_phase(const gemm::Phase& ph, const Problem* dev, cudaStream_t st) {
+  if (ph.count == 0) return PPB_OK;
+  int grid = ph.tiles < 8 * PPB_NUM_SMS ? ph.tiles : 8 * PPB_NUM_SMS;
+  gemm::k_grouped<<<grid, gemm::kThreads, 0, st>>>(dev + ph.first, ph.count, ph.tiles);
+  PPB_LAUNCH_CHECK();
+  return PPB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// element-wise / fused kernels
+// ---------------------------------------------------------------------------------------------------
+// step embedding rows: [prev_type | prev_addr | cur_type | cur_addr] (inference_network_lstm.py:175-180)
+__global__ void k_step_embed(const float* __restrict__ arena, const ppb_addr_desc* __restrict__ addrs,
+                             const int64_t* __restrict__ type_off, const int* __restrict__ step_addr,
+                             const int* __restrict__ step_prev, int n_steps, int td, int ad,
+                             float* __restrict__ emb_cat) {
+  int C2 = 2 * (td + ad);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (int64_t)n_steps * C2;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    int st = (int)(e / C2), j = (int)(e % C2);
+    int which = j < (td + ad) ? step_prev[st] : step_addr[st];
+    int jj = j < (td + ad) ? j : j - (td + ad);
+    float v = 0.0f;
+    if (which >= 0) {
+      const ppb_addr_desc& a = addrs[which];
+      v = jj < td ? arena[type_off[a.type_id] + jj] : arena[a.addr_emb_off + (jj - td)];
+    }
+    emb_cat[e] = v;
+  }
+}
+
+// transposed copy of the sample-embedding columns of W_ih: w_smp_t[j][col] = W_ih[col, E + j]
+__global__ void k_wsmp_transpose(const float* __restrict__ w_ih, int I, int E, int S, int H4,
+                                 float* __restrict__ w_smp_t) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < S * H4; e += gridDim.x * blockDim.x) {
+    int j = e / H4, col = e % H4;
+    w_smp_t[e] = w_ih[(int64_t)col * I + E + j];
+  }
+}
+
+// previous-sample embedding per row: relu(W_se[prev_addr] x + b), x = value or one-hot(value)
+// (inference_network_lstm.py:168-169, embedding_feedforward.py:35-48); zeros at t = 0 (:157)
+__global__ void k_smp_embed(const float* __restrict__ arena, const ppb_addr_desc* __restrict__ addrs,
+                            const int* __restrict__ row_step, const int* __restrict__ step_prev,
+                            const int* __restrict__ row_prev, const float* __restrict__ values, int R, int S,
+                            float* __restrict__ smp_emb) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (int64_t)R * S;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    int row = (int)(e / S), j = (int)(e % S);
+    int pa = step_prev[row_step[row]];
+    float v = 0.0f;
+    if (pa >= 0) {
+      const ppb_addr_desc& a = addrs[pa];
+      float x = values[row_prev[row]];
+      const float* W = arena + a.smp_w_off + (int64_t)j * a.smp_in;
+      float pre = arena[a.smp_b_off + j];
+      if (a.family == PPB_FAMILY_CATEGORICAL) {
+        int c = (int)x;
+        if (c >= 0 && c < a.smp_in) pre += W[c];
+      } else {
+        pre += W[0] * x;
+      }
+      v = fmaxf(pre, 0.0f);
+    }
+    smp_emb[e] = v;
+  }
+}
+
+// LSTM cell, one time step, all active rows (torch.nn.LSTM gate order i,f,g,o; h0 = c0 = 0, :186-187)
+__global__ void __launch_bounds__(256) k_cell_fwd(float* __restrict__ gates, const float* __restrict__ p_obs,
+                                                   const float* __restrict__ p_step, const float* __restrict__ w_smp_t,
+                                                   const float* __restrict__ smp_emb, const int* __restrict__ row_step,
+                                                   const int* __restrict__ row_prev, float* __restrict__ c,
+                                                   float* __restrict__ h, int row0, int n_rows, int H, int S, int t) {
+  int64_t total = (int64_t)n_rows * H;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int i = (int)(e / H), j = (int)(e % H);
+    int row = row0 + i;
+    int st = row_step[row];
+    float pre[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      int col = g * H + j;
+      float v = p_obs[(int64_t)i * 4 * H + col] + p_step[(int64_t)st * 4 * H + col];
+      if (t > 0) {
+        v += gates[(int64_t)row * 4 * H + col];  // recurrent part written by the GEMM
+        for (int s = 0; s < S; ++s) v = fmaf(smp_emb[(int64_t)row * S + s], w_smp_t[(int64_t)s * 4 * H + col], v);
+      }
+      pre[g] = v;
+    }
+    float ig = 1.0f / (1.0f + expf(-pre[0]));
+    float fg = 1.0f / (1.0f + expf(-pre[1]));
+    float gg = tanhf(pre[2]);
+    float og = 1.0f / (1.0f + expf(-pre[3]));
+    float cp = (t > 0) ? c[(int64_t)row_prev[row] * H + j] : 0.0f;
+    float cn = fg * cp + ig * gg;
+    float hn = og * tanhf(cn);
+    gates[(int64_t)row * 4 * H + j] = ig;
+    gates[(int64_t)row * 4 * H + H + j] = fg;
+    gates[(int64_t)row * 4 * H + 2 * H + j] = gg;
+    gates[(int64_t)row * 4 * H + 3 * H + j] = og;
+    c[(int64_t)row * H + j] = cn;
+    h[(int64_t)row * H + j] = hn;
+  }
+}
+
+// heads: family transform + log q(value) + d(-log q)/d out, loss reduction (:199-218)
+__global__ void __launch_bounds__(128) k_head_nll(const float* __restrict__ out_raw, int out_pad,
+                                                   const ppb_addr_desc* __restrict__ addrs,
+                                                   const int* __restrict__ row_step, const int* __restrict__ step_addr,
+                                                   const float* __restrict__ values, const float* __restrict__ prior0,
+                                                   const float* __restrict__ prior1, int R, int K, float inv_batch,
+                                                   float* __restrict__ row_lp, float* __restrict__ d_out,
+                                                   float* __restrict__ loss_acc) {
+  float local = 0.0f;
+  int bad = 0;
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < R; row += gridDim.x * blockDim.x) {
+    const ppb_addr_desc& a = addrs[step_addr[row_step[row]]];
+    const float* x = out_raw + (int64_t)row * out_pad;
+    float xs[heads::CMAX > 3 * heads::KMAX ? heads::CMAX : 3 * heads::KMAX];
+    float gx[heads::CMAX > 3 * heads::KMAX ? heads::CMAX : 3 * heads::KMAX];
+    int O = a.head_out;
+    for (int j = 0; j < O; ++j) xs[j] = x[j];
+    float lp;
+    if (a.family == PPB_FAMILY_CATEGORICAL)
+      lp = heads::categorical_nll(xs, a.num_categories, values[row], gx, d_out != nullptr);
+    else
+      lp = heads::mixture_nll(a.family, xs, K, prior0[row], prior1[row], values[row], gx, d_out != nullptr);
+    if (lp == -INFINITY) lp = PPB_LOG_EPSILON;       // util.replace_negative_inf (:213), zero gradient
+    if (isnan(lp) || isinf(lp)) { bad += 1; lp = 0.0f; for (int j = 0; j < O; ++j) gx[j] = 0.0f; }
+    if (row_lp) row_lp[row] = lp;
+    local += -lp;
+    if (d_out)
+      for (int j = 0; j < O; ++j) d_out[(int64_t)row * out_pad + j] = gx[j] * inv_batch;
+  }
+  local = ppb_warp_sum(local);
+  bad = __reduce_add_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0) {
+    if (local != 0.0f) atomicAdd(loss_acc, local * inv_batch);
+    if (bad) atomicAdd(reinterpret_cast<int*>(loss_acc + 1), bad);
+  }
+}
+
+__global__ void k_publish_loss(const float* __restrict__ loss_acc, float* __restrict__ loss_out,
+                               int* __restrict__ status_out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (loss_out) *loss_out = loss_acc[0];
+    if (status_out) *status_out = *reinterpret_cast<const int*>(loss_acc + 1);
+  }
+}
+
+// LSTM cell backward, one time step (reverse order).  dgates rows of this step are produced here;
+// dh_rec = dgates[t+1] W_hh (prefix of this step's rows), dc carries d c_t across steps.
+__global__ void __launch_bounds__(256) k_cell_bwd(const float* __restrict__ gates, const float* __restrict__ c,
+                                                   const float* __restrict__ dh, const float* __restrict__ dh_rec,
+                                                   float* __restrict__ dc, float* __restrict__ dgates,
+                                                   float* __restrict__ d_pobs, const int* __restrict__ row_prev,
+                                                   int row0, int n_rows, int n_next, int H, int t) {
+  int64_t total = (int64_t)n_rows * H;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int i = (int)(e / H), j = (int)(e % H);
+    int row = row0 + i;
+    const float* g = gates + (int64_t)row * 4 * H;
+    float ig = g[j], fg = g[H + j], gg = g[2 * H + j], og = g[3 * H + j];
+    float cn = c[(int64_t)row * H + j];
+    float cp = (t > 0) ? c[(int64_t)row_prev[row] * H + j] : 0.0f;
+    float tc = tanhf(cn);
+    bool has_next = i < n_next;
+    float dht = dh[(int64_t)row * H + j] + (has_next ? dh_rec[(int64_t)i * H + j] : 0.0f);
+    float dct = (has_next ? dc[(int64_t)i * H + j] : 0.0f) + dht * og * (1.0f - tc * tc);
+    float di = dct * gg * ig * (1.0f - ig);
+    float df = dct * cp * fg * (1.0f - fg);
+    float dg = dct * ig * (1.0f - gg * gg);
+    float d_o = dht * tc * og * (1.0f - og);
+    dc[(int64_t)i * H + j] = dct * fg;
+    float* dgr = dgates + (int64_t)row * 4 * H;
+    dgr[j] = di; dgr[H + j] = df; dgr[2 * H + j] = dg; dgr[3 * H + j] = d_o;
+    float* dp = d_pobs + (int64_t)i * 4 * H;
+    if (has_next) { dp[j] += di; dp[H + j] += df; dp[2 * H + j] += dg; dp[3 * H + j] += d_o; }
+    else { dp[j] = di; dp[H + j] = df; dp[2 * H + j] = dg; dp[3 * H + j] = d_o; }
+  }
+}
+
+// d_pstep[st, col] = sum over the rows of step st (contiguous range) of dgates[row, col]
+__global__ void k_step_colsum(const float* __restrict__ dgates, const int* __restrict__ step_row0,
+                              const int* __restrict__ step_nrows, int H4, float* __restrict__ d_pstep) {
+  int st = blockIdx.y;
+  int r0 = step_row0[st], n = step_nrows[st];
+  for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < H4; col += gridDim.x * blockDim.x) {
+    float s = 0.0f;
+    for (int r = 0; r < n; ++r) s += dgates[(int64_t)(r0 + r) * H4 + col];
+    d_pstep[(int64_t)st * H4 + col] = s;
+  }
+}
+
+// d_smp[row, j] = sum_col dgates[row, col] * w_smp_t[j][col], masked by relu; then the per-address
+// sample-embedding layer gradients (atomics on tiny [S x smp_in] matrices)
+__global__ void __launch_bounds__(128) k_smp_bwd(const float* __restrict__ dgates, const float* __restrict__ w_smp_t,
+                                                  const float* __restrict__ smp_emb, const float* __restrict__ values,
+                                                  const int* __restrict__ row_step, const int* __restrict__ step_prev,
+                                                  const int* __restrict__ row_prev,
+                                                  const ppb_addr_desc* __restrict__ addrs, int R, int H4, int S,
+                                                  float* __restrict__ grad) {
+  // one warp per row
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = warp; row < R; row += nwarps) {
+    int pa = step_prev[row_step[row]];
+    if (pa < 0) continue;
+    const ppb_addr_desc& a = addrs[pa];
+    float x = values[row_prev[row]];
+    for (int j = 0; j < S; ++j) {
+      float s = 0.0f;
+      for (int col = lane; col < H4; col += 32) s = fmaf(dgates[(int64_t)row * H4 + col], w_smp_t[(int64_t)j * H4 + col], s);
+      s = ppb_warp_sum(s);
+      if (lane == 0 && smp_emb[(int64_t)row * S + j] > 0.0f && s != 0.0f) {
+        atomicAdd(grad + a.smp_b_off + j, s);
+        if (a.family == PPB_FAMILY_CATEGORICAL) {
+          int cidx = (int)x;
+          if (cidx >= 0 && cidx < a.smp_in) atomicAdd(grad + a.smp_w_off + (int64_t)j * a.smp_in + cidx, s);
+        } else {
+          atomicAdd(grad + a.smp_w_off + (int64_t)j * a.smp_in, s * x);
+        }
+      }
+    }
+  }
+}
+
+// dW_ih[:, E + j] += sum_rows dgates[row, col] * smp_emb[row, j]
+__global__ void k_wsmp_grad(const float* __restrict__ dgates, const float* __restrict__ smp_emb, int R, int H4, int S,
+                            int I, int E, float* __restrict__ dw_ih, int rows_per_block) {
+  int r0 = blockIdx.y * rows_per_block;
+  int r1 = r0 + rows_per_block < R ? r0 + rows_per_block : R;
+  for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < H4; col += gridDim.x * blockDim.x) {
+    float acc[8];
+    for (int j = 0; j < S; ++j) acc[j] = 0.0f;
+    for (int r = r0; r < r1; ++r) {
+      float d = dgates[(int64_t)r * H4 + col];
+      for (int j = 0; j < S; ++j) acc[j] = fmaf(d, smp_emb[(int64_t)r * S + j], acc[j]);
+    }
+    for (int j = 0; j < S; ++j)
+      if (acc[j] != 0.0f) atomicAdd(dw_ih + (int64_t)col * I + E + j, acc[j]);
+  }
+}
+
+// biases: db_ih = db_hh = column sums of d_pstep ; scatter d_embcat into the embedding tables
+__global__ void k_bias_grad(const float* __restrict__ d_pstep, int NS, int H4, float* __restrict__ db_ih,
+                            float* __restrict__ db_hh) {
+  for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < H4; col += gridDim.x * blockDim.x) {
+    float s = 0.0f;
+    for (int st = 0; st < NS; ++st) s += d_pstep[(int64_t)st * H4 + col];
+    db_ih[col] += s;
+    db_hh[col] += s;
+  }
+}
+__global__ void k_embed_scatter(const float* __restrict__ d_embcat, const ppb_addr_desc* __restrict__ addrs,
+                                const int64_t* __restrict__ type_off, const int* __restrict__ step_addr,
+                                const int* __restrict__ step_prev, int n_steps, int td, int ad,
+                                float* __restrict__ grad) {
+  int C2 = 2 * (td + ad);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (int64_t)n_steps * C2;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    int st = (int)(e / C2), j = (int)(e % C2);
+    int which = j < (td + ad) ? step_prev[st] : step_addr[st];
+    int jj = j < (td + ad) ? j : j - (td + ad);
+    if (which < 0) continue;
+    const ppb_addr_desc& a = addrs[which];
+    float v = d_embcat[e];
+    if (v == 0.0f) continue;
+    if (jj < td) atomicAdd(grad + type_off[a.type_id] + jj, v);
+    else atomicAdd(grad + a.addr_emb_off + (jj - td), v);
+  }
+}
+// bias gradient of a Linear: db[n] += sum_m dY[gm(m), n]
+__global__ void k_colsum_gather(const float* __restrict__ dY, int64_t ld, const int* __restrict__ m_gather, int M,
+                                int N, float* __restrict__ db) {
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+    float s = 0.0f;
+    for (int m = 0; m < M; ++m) {
+      int64_t pm = m_gather ? m_gather[m] : m;
+      s += dY[pm * ld + n];
+    }
+    db[n] += s;
+  }
+}
+__global__ void k_scale(float* __restrict__ x, int64_t n, float a) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] *= a;
+}
+
+// p[i] += b[i mod H4]  (fold b_hh into the step projection, which already carries b_ih)
+__global__ void k_add_row_bias(float* __restrict__ p, const float* __restrict__ b, int64_t n, int H4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] += b[i % H4];
+}
+// ReLU backward at the top of a chain: d[i] = y[i] > 0 ? d[i] : 0
+__global__ void k_mask_nonpos(float* __restrict__ d, const float* __restrict__ y, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (!(y[i] > 0.0f)) d[i] = 0.0f;
+}
+
+inline int ew_grid(int64_t n, int threads = 256) { return ppb_grid_for(n, threads, 1); }
+
+Dims dims_of(const ppb_batch* b) {
+  Dims d; d.B = b->n_traces; d.R = b->n_rows; d.T = b->t_max; d.NS = b->n_steps; d.G = b->n_groups;
+  return d;
+}
+
+int check_batch(const ppb_net* net, const ppb_batch* b) {
+  PPB_CHECK_ARG(net && b, "null net or batch");
+  PPB_CHECK_ARG(b->n_traces > 0 && b->n_rows > 0 && b->t_max > 0 && b->n_steps > 0 && b->n_groups > 0, "empty batch");
+  PPB_CHECK_ARG(b->row_off_host && b->group_addr_host && b->group_start_host, "missing host arrays");
+  PPB_CHECK_ARG(b->row_off_host[0] == 0 && b->row_off_host[b->t_max] == b->n_rows, "row_off inconsistent");
+  for (int g = 0; g < b->n_groups; ++g)
+    PPB_CHECK_ARG(b->group_addr_host[g] >= 0 && b->group_addr_host[g] < (int)net->addrs.size(), "address id out of range");
+  return PPB_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int ppb_net_create(ppb_net** out, const ppb_net_desc* d) {
+  PPB_CHECK_ARG(out && d, "null argument");
+  PPB_CHECK_ARG(d->lstm_dim > 0 && d->obs_dim > 0 && d->sample_dim > 0 && d->sample_dim <= 8, "bad dims");
+  PPB_CHECK_ARG(d->num_obs > 0 && d->num_obs <= PPB_MAX_OBS, "bad observable count");
+  PPB_CHECK_ARG(d->mixture_k > 0 && d->mixture_k <= heads::KMAX, "mixture components must be in [1,32]");
+  ppb_net* n = new ppb_net();
+  n->desc = *d;
+  n->I = d->obs_dim + d->sample_dim + 2 * (d->type_dim + d->addr_dim);
+  *out = n;
+  return PPB_OK;
+}
+
+int ppb_net_set_tables(ppb_net* net, const ppb_addr_desc* addrs, int32_t n_addrs, const int64_t* type_off,
+                       int32_t n_types, int64_t arena_floats) {
+  PPB_CHECK_ARG(net && addrs && type_off && n_addrs > 0 && n_types > 0, "bad arguments");
+  net->addrs.assign(addrs, addrs + n_addrs);
+  net->type_off.assign(type_off, type_off + n_types);
+  net->arena_floats = arena_floats;
+  int dh = 4, op = 4;
+  for (auto& a : net->addrs) {
+    PPB_CHECK_ARG(a.family >= 0 && a.family <= 3, "unknown family");
+    PPB_CHECK_ARG(a.family != PPB_FAMILY_CATEGORICAL || (a.num_categories > 0 && a.num_categories <= heads::CMAX),
+                  "categorical head: 1..128 categories supported");
+    PPB_CHECK_ARG(a.type_id >= 0 && a.type_id < n_types, "type id out of range");
+    if (a.head_hidden > dh) dh = a.head_hidden;
+    if (a.head_out > op) op = a.head_out;
+  }
+  net->dh_pad = (int)align_up(dh, 4);
+  net->out_pad = (int)align_up(op, 4);
+  if (net->d_addrs) cudaFree(net->d_addrs);
+  if (net->d_type_off) cudaFree(net->d_type_off);
+  PPB_CUDA(cudaMalloc((void**)&net->d_addrs, sizeof(ppb_addr_desc) * n_addrs));
+  PPB_CUDA(cudaMalloc((void**)&net->d_type_off, sizeof(int64_t) * n_types));
+  PPB_CUDA(cudaMemcpy(net->d_addrs, addrs, sizeof(ppb_addr_desc) * n_addrs, cudaMemcpyHostToDevice));
+  PPB_CUDA(cudaMemcpy(net->d_type_off, type_off, sizeof(int64_t) * n_types, cudaMemcpyHostToDevice));
+  return PPB_OK;
+}
+
+int ppb_net_destroy(ppb_net* net) {
+  if (!net) return PPB_OK;
+  if (net->d_addrs) cudaFree(net->d_addrs);
+  if (net->d_type_off) cudaFree(net->d_type_off);
+  for (int i = 0; i < 2; ++i) {
+    if (net->h_stage[i]) cudaFreeHost(net->h_stage[i]);
+    if (net->ev_stage[i]) cudaEventDestroy(net->ev_stage[i]);
+  }
+  delete net;
+  return PPB_OK;
+}
+
+int64_t ppb_ic_workspace_bytes(const ppb_net* net, int32_t n_traces, int32_t n_rows, int32_t t_max, int32_t n_steps,
+                               int32_t n_groups) {
+  if (!net || n_traces <= 0 || n_rows <= 0) return -1;
+  Dims d; d.B = n_traces; d.R = n_rows; d.T = t_max; d.NS = n_steps; d.G = n_groups;
+  Ws w = carve(net, d, nullptr);
+  return w.total_bytes + dgates_bytes(net, d) + 1024;
+}
+
+int ppb_ic_loss_forward(ppb_net* net, const float* arena, const ppb_batch* b, void* workspace,
+                        int64_t workspace_bytes, int precision, float* loss_out, int32_t* status_out,
+                        float* row_lp_out, int want_grad, void* stream) {
+  int rc = check_batch(net, b);
+  if (rc) return rc;
+  PPB_CHECK_ARG(arena && workspace, "null arena/workspace");
+  PPB_CHECK_ARG(!net->addrs.empty(), "address tables not set");
+  (void)precision;
+  const ppb_net_desc& D = net->desc;
+  Dims d = dims_of(b);
+  PPB_CHECK_ARG(workspace_bytes >= ppb_ic_workspace_bytes(net, d.B, d.R, d.T, d.NS, d.G), "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  Ws w = carve(net, d, workspace);
+  const int H = D.lstm_dim, H4 = 4 * H, E = D.obs_dim, S = D.sample_dim, I = net->I;
+  const int C2 = 2 * (D.type_dim + D.addr_dim);
+
+  // ---- problem lists for all forward GEMM phases -------------------------------------------------
+  Builder bl;
+  add_obs_embed(bl, D, arena, b->obs, d.B, w.obs_act, w.obs_cat, w.fin_act, w.obs_emb);
+  const int ph_obs0 = 0;
+  const int ph_p = (int)bl.phases.size();
+  bl.begin();
+  bl.add(linear_fwd(w.obs_emb, E, arena + D.w_ih_off, I, nullptr, w.p_obs, H4, d.B, H4, E, 0));
+  bl.add(linear_fwd(w.emb_cat, C2, arena + D.w_ih_off + E + S, I, arena + D.b_ih_off, w.p_step, H4, d.NS, H4, C2, 0));
+  // recurrent GEMMs: gates[rows of t] = h[rows of t-1 (prefix)] W_hh^T
+  const int ph_rec0 = (int)bl.phases.size();
+  for (int t = 1; t < d.T; ++t) {
+    bl.begin();
+    int r0 = b->row_off_host[t], n = b->row_off_host[t + 1] - r0, rp = b->row_off_host[t - 1];
+    bl.add(linear_fwd(w.h + (int64_t)rp * H, H, arena + D.w_hh_off, H, nullptr, w.gates + (int64_t)r0 * H4, H4, n, H4, H, 0));
+  }
+  const int ph_h1 = (int)bl.phases.size();
+  bl.begin();
+  for (int g = 0; g < d.G; ++g) {
+    const ppb_addr_desc& a = net->addrs[b->group_addr_host[g]];
+    int s0 = b->group_start_host[g], cnt = b->group_start_host[g + 1] - s0;
+    Problem p = linear_fwd(w.h, H, arena + a.w1_off, H, arena + a.b1_off, w.hid, net->dh_pad, cnt, a.head_hidden, H, gemm::kRelu);
+    p.m_gather = b->head_rows + s0;
+    bl.add(p);
+  }
+  const int ph_h2 = (int)bl.phases.size();
+  bl.begin();
+  for (int g = 0; g < d.G; ++g) {
+    const ppb_addr_desc& a = net->addrs[b->group_addr_host[g]];
+    int s0 = b->group_start_host[g], cnt = b->group_start_host[g + 1] - s0;
+    Problem p = linear_fwd(w.hid, net->dh_pad, arena + a.w2_off, a.head_hidden, arena + a.b2_off, w.out_raw, net->out_pad, cnt, a.head_out, a.head_hidden, 0);
+    p.m_gather = b->head_rows + s0;
+    bl.add(p);
+  }
+  rc = upload_and_get(net, bl, w.problems, w.max_problems, st);
+  if (rc) return rc;
+
+  // ---- launches -----------------------------------------------------------------------------------
+  PPB_CUDA(cudaMemsetAsync(w.loss_acc, 0, 256, st));
+  for (int l = ph_obs0; l < ph_p; ++l) { rc = run_phase(bl.phases[l], w.problems, st); if (rc) return rc; }
+  k_step_embed<<<ew_grid((int64_t)d.NS * C2), 256, 0, st>>>(arena, net->d_addrs, net->d_type_off, b->step_addr,
+                                                            b->step_prev_addr, d.NS, D.type_dim, D.addr_dim, w.emb_cat);
+  PPB_LAUNCH_CHECK();
+  k_wsmp_transpose<<<ew_grid(S * H4), 256, 0, st>>>(arena + D.w_ih_off, I, E, S, H4, w.w_smp_t);
+  PPB_LAUNCH_CHECK();
+  k_smp_embed<<<ew_grid((int64_t)d.R * S), 256, 0, st>>>(arena, net->d_addrs, b->row_step, b->step_prev_addr,
+                                                         b->row_prev, b->values, d.R, S, w.smp_emb);
+  PPB_LAUNCH_CHECK();
+  rc = run_phase(bl.phases[ph_p], w.problems, st);
+  if (rc) return rc;
+  // b_hh joins the step projection (P_step already has b_ih): add once with a scaled-axpy kernel
+  k_add_row_bias<<<ew_grid((int64_t)d.NS * H4), 256, 0, st>>>(w.p_step, arena + D.b_hh_off, (int64_t)d.NS * H4, H4);
+  PPB_LAUNCH_CHECK();
+  for (int t = 0; t < d.T; ++t) {
+    int r0 = b->row_off_host[t], n = b->row_off_host[t + 1] - r0;
+    if (t > 0) { rc = run_phase(bl.phases[ph_rec0 + t - 1], w.problems, st); if (rc) return rc; }
+    k_cell_fwd<<<ew_grid((int64_t)n * H), 256, 0, st>>>(w.gates, w.p_obs, w.p_step, w.w_smp_t, w.smp_emb, b->row_step,
+                                                       b->row_prev, w.c, w.h, r0, n, H, S, t);
+    PPB_LAUNCH_CHECK();
+  }
+  rc = run_phase(bl.phases[ph_h1], w.problems, st); if (rc) return rc;
+  rc = run_phase(bl.phases[ph_h2], w.problems, st); if (rc) return rc;
+  k_head_nll<<<ew_grid(d.R, 128), 128, 0, st>>>(w.out_raw, net->out_pad, net->d_addrs, b->row_step, b->step_addr,
+                                                b->values, b->prior0, b->prior1, d.R, D.mixture_k, 1.0f / (float)d.B,
+                                                row_lp_out ? row_lp_out : w.row_lp, want_grad ? w.d_out : nullptr,
+                                                w.loss_acc);
+  PPB_LAUNCH_CHECK();
+  k_publish_loss<<<1, 32, 0, st>>>(w.loss_acc, loss_out, status_out);
+  PPB_LAUNCH_CHECK();
+  return PPB_OK;
+}
+
+int ppb_ic_loss_backward(ppb_net* net, const float* arena, float* grad, const ppb_batch* b, void* workspace,
+                         int64_t workspace_bytes, int precision, float grad_scale, void* stream) {
+  int rc = check_batch(net, b);
+  if (rc) return rc;
+  PPB_CHECK_ARG(arena && grad && workspace, "null arena/grad/workspace");
+  (void)precision;
+  const ppb_net_desc& D = net->desc;
+  Dims d = dims_of(b);
+  PPB_CHECK_ARG(workspace_bytes >= ppb_ic_workspace_bytes(net, d.B, d.R, d.T, d.NS, d.G), "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  Ws w = carve(net, d, workspace);
+  float* dgates = dgates_ptr(w, workspace);
+  const int H = D.lstm_dim, H4 = 4 * H, E = D.obs_dim, S = D.sample_dim, I = net->I;
+  const int C2 = 2 * (D.type_dim + D.addr_dim);
+
+  if (grad_scale != 1.0f) {
+    k_scale<<<ew_grid((int64_t)d.R * net->out_pad), 256, 0, st>>>(w.d_out, (int64_t)d.R * net->out_pad, grad_scale);
+    PPB_LAUNCH_CHECK();
+  }
+
+  Builder bl;
+  // heads: d_hid = (d_out W2) * relu'(hid) ; dW2 += d_out^T hid ; dh = d_hid W1 ; dW1 += d_hid^T h
+  const int ph_dhid = 0;
+  bl.begin();
+  for (int g = 0; g < d.G; ++g) {
+    const ppb_addr_desc& a = net->addrs[b->group_addr_host[g]];
+    int s0 = b->group_start_host[g], cnt = b->group_start_host[g + 1] - s0;
+    Problem p = linear_dx(w.d_out, net->out_pad, arena + a.w2_off, a.head_hidden, w.d_hid, net->dh_pad, cnt, a.head_out, a.head_hidden, gemm::kMaskAux);
+    p.aux = w.hid; p.ld_aux = net->dh_pad; p.m_gather = b->head_rows + s0;
+    bl.add(p);
+  }
+  const int ph_hw = 1;
+  bl.begin();
+  for (int g = 0; g < d.G; ++g) {
+    const ppb_addr_desc& a = net->addrs[b->group_addr_host[g]];
+    int s0 = b->group_start_host[g], cnt = b->group_start_host[g + 1] - s0;
+    Problem p2 = linear_dw(w.d_out, net->out_pad, w.hid, net->dh_pad, grad + a.w2_off, a.head_hidden, cnt, a.head_out, a.head_hidden);
+    p2.ka_gather = b->head_rows + s0; p2.kb_gather = b->head_rows + s0;
+    bl.add(p2);
+    Problem p1 = linear_dw(w.d_hid, net->dh_pad, w.h, H, grad + a.w1_off, H, cnt, a.head_hidden, H);
+    p1.ka_gather = b->head_rows + s0; p1.kb_gather = b->head_rows + s0;
+    bl.add(p1);
+    Problem px = linear_dx(w.d_hid, net->dh_pad, arena + a.w1_off, H, w.dh, H, cnt, a.head_hidden, H, 0);
+    px.m_gather = b->head_rows + s0;
+    bl.add(px);
+  }
+  // BPTT recurrent: dh_rec[prefix rows of t-1] = dgates[rows of t] W_hh
+  const int ph_rec0 = 2;
+  for (int t = d.T - 1; t >= 1; --t) {
+    bl.begin();
+    int r0 = b->row_off_host[t], n = b->row_off_host[t + 1] - r0;
+    bl.add(linear_dx(dgates + (int64_t)r0 * H4, H4, arena + D.w_hh_off, H, w.dh_rec, H, n, H4, H, 0));
+  }
+  const int ph_lstm_w = (int)bl.phases.size();
+  bl.begin();
+  {
+    // dW_hh += sum_{rows t>=1} dgates[row]^T h[row_prev[row]]
+    int r1 = b->row_off_host[1 < d.T ? 1 : d.T];
+    int n1 = d.R - r1;
+    if (n1 > 0) {
+      Problem p = linear_dw(dgates + (int64_t)r1 * H4, H4, w.h, H, grad + D.w_hh_off, H, n1, H4, H);
+      p.kb_gather = b->row_prev + r1;  // h row of the previous step
+      bl.add(p);
+    }
+    // dW_ih[:, :E] += d_pobs^T obs_emb ; dW_ih[:, E+S:] += d_pstep^T emb_cat
+    bl.add(linear_dw(w.d_pobs, H4, w.obs_emb, E, grad + D.w_ih_off, I, d.B, H4, E));
+    bl.add(linear_dw(w.d_pstep, H4, w.emb_cat, C2, grad + D.w_ih_off + E + S, I, d.NS, H4, C2));
+    // d obs_emb = d_pobs W_ih[:, :E] ; d emb_cat = d_pstep W_ih[:, E+S:]
+    bl.add(linear_dx(w.d_pobs, H4, arena + D.w_ih_off, I, w.d_obs_emb, E, d.B, H4, E, 0));
+    bl.add(linear_dx(w.d_pstep, H4, arena + D.w_ih_off + E + S, I, w.d_embcat, C2, d.NS, H4, C2, 0));
+  }
+  // observe-embedding final FF backward (each layer: mask by relu, dW, dX)
+  std::vector<int> ph_fin;
+  for (int l = D.obs_final.num_layers - 1; l >= 0; --l) {
+    const ppb_linear_desc& L = D.obs_final.layers[l];
+    const float* X = l == 0 ? w.obs_cat : w.fin_act[l - 1];
+    float* dY = (l == D.obs_final.num_layers - 1) ? w.d_obs_emb : w.d_fin_act[l];
+    float* dX = l == 0 ? w.d_obs_cat : w.d_fin_act[l - 1];
+    ph_fin.push_back((int)bl.phases.size());
+    bl.begin();
+    bl.add(linear_dw(dY, L.out_dim, X, L.in_dim, grad + L.w_off, L.in_dim, d.B, L.out_dim, L.in_dim));
+    Problem px = linear_dx(dY, L.out_dim, arena + L.w_off, L.in_dim, dX, L.in_dim, d.B, L.out_dim, L.in_dim, gemm::kMaskAux);
+    px.aux = X; px.ld_aux = L.in_dim;  // relu' of the layer below: its output is this layer's input
+    if (l == 0) { px.aux = w.obs_cat; px.ld_aux = E; }
+    bl.add(px);
+  }
+  // per-observable FF backward by depth level (from the top)
+  int max_depth = 0;
+  for (int j = 0; j < D.num_obs; ++j) max_depth = D.obs_ff[j].num_layers > max_depth ? D.obs_ff[j].num_layers : max_depth;
+  std::vector<int> in_off(D.num_obs), out_off(D.num_obs);
+  { int ci = 0, co = 0; for (int j = 0; j < D.num_obs; ++j) { in_off[j] = ci; out_off[j] = co; ci += D.obs_ff[j].in_dim; co += D.obs_ff[j].out_dim; } }
+  std::vector<int> ph_obs;
+  for (int l = max_depth - 1; l >= 0; --l) {
+    ph_obs.push_back((int)bl.phases.size());
+    bl.begin();
+    for (int j = 0; j < D.num_obs; ++j) {
+      const ppb_ff_desc& ff = D.obs_ff[j];
+      if (l >= ff.num_layers) continue;
+      const ppb_linear_desc& L = ff.layers[l];
+      bool last = (l == ff.num_layers - 1);
+      const float* X = l == 0 ? b->obs + in_off[j] : w.obs_act[j][l - 1];
+      int64_t ldx = l == 0 ? D.obs_in_total : ff.layers[l - 1].out_dim;
+      const float* dY = last ? w.d_obs_cat + out_off[j] : w.d_obs_act[j][l];
+      int64_t lddy = last ? E : L.out_dim;
+      bl.add(linear_dw(dY, lddy, X, ldx, grad + L.w_off, L.in_dim, d.B, L.out_dim, L.in_dim));
+      if (l > 0) {
+        Problem px = linear_dx(dY, lddy, arena + L.w_off, L.in_dim, w.d_obs_act[j][l - 1], ff.layers[l - 1].out_dim, d.B, L.out_dim, L.in_dim, gemm::kMaskAux);
+        px.aux = w.obs_act[j][l - 1]; px.ld_aux = ff.layers[l - 1].out_dim;
+        bl.add(px);
+      }
+    }
+  }
+  rc = upload_and_get(net, bl, w.problems, w.max_problems, st);
+  if (rc) return rc;
+
+  // ---- launches -----------------------------------------------------------------------------------
+  rc = run_phase(bl.phases[ph_dhid], w.problems, st); if (rc) return rc;
+  rc = run_phase(bl.phases[ph_hw], w.problems, st); if (rc) return rc;
+  // head bias gradients
+  for (int g = 0; g < d.G; ++g) {
+    const ppb_addr_desc& a = net->addrs[b->group_addr_host[g]];
+    int s0 = b->group_start_host[g], cnt = b->group_start_host[g + 1] - s0;
+    k_colsum_gather<<<(a.head_out + 127) / 128, 128, 0, st>>>(w.d_out, net->out_pad, b->head_rows + s0, cnt, a.head_out, grad + a.b2_off);
+    k_colsum_gather<<<(a.head_hidden + 127) / 128, 128, 0, st>>>(w.d_hid, net->dh_pad, b->head_rows + s0, cnt, a.head_hidden, grad + a.b1_off);
+  }
+  PPB_LAUNCH_CHECK();
+  // BPTT
+  for (int t = d.T - 1; t >= 0; --t) {
+    int r0 = b->row_off_host[t], n = b->row_off_host[t + 1] - r0;
+    int n_next = (t + 1 < d.T) ? b->row_off_host[t + 2] - b->row_off_host[t + 1] : 0;
+    if (n_next > 0) { rc = run_phase(bl.phases[ph_rec0 + (d.T - 2 - t)], w.problems, st); if (rc) return rc; }
+    k_cell_bwd<<<ew_grid((int64_t)n * H), 256, 0, st>>>(w.gates, w.c, w.dh, w.dh_rec, w.dc, dgates, w.d_pobs, b->row_prev,
+                                                       r0, n, n_next, H, t);
+    PPB_LAUNCH_CHECK();
+  }
+  {
+    dim3 g((H4 + 255) / 256, d.NS);
+    k_step_colsum<<<g, 256, 0, st>>>(dgates, b->step_row0, b->step_nrows, H4, w.d_pstep);
+    PPB_LAUNCH_CHECK();
+  }
+  rc = run_phase(bl.phases[ph_lstm_w], w.problems, st); if (rc) return rc;
+  k_bias_grad<<<(H4 + 255) / 256, 256, 0, st>>>(w.d_pstep, d.NS, H4, grad + D.b_ih_off, grad + D.b_hh_off);
+  PPB_LAUNCH_CHECK();
+  k_embed_scatter<<<ew_grid((int64_t)d.NS * C2), 256, 0, st>>>(w.d_embcat, net->d_addrs, net->d_type_off, b->step_addr,
+                                                               b->step_prev_addr, d.NS, D.type_dim, D.addr_dim, grad);
+  PPB_LAUNCH_CHECK();
+  if (d.T > 1) {
+    k_smp_bwd<<<ew_grid((int64_t)d.R * 32, 128), 128, 0, st>>>(dgates, w.w_smp_t, w.smp_emb, b->values, b->row_step,
+                                                              b->step_prev_addr, b->row_prev, net->d_addrs, d.R, H4, S, grad);
+    PPB_LAUNCH_CHECK();
+    int rpb = 256;
+    dim3 g((H4 + 255) / 256, (d.R + rpb - 1) / rpb);
+    k_wsmp_grad<<<g, 256, 0, st>>>(dgates, w.smp_emb, d.R, H4, S, I, E, grad + D.w_ih_off, rpb);
+    PPB_LAUNCH_CHECK();
+  }
+  // observe embedding backward; relu' of the final output masks d_obs_emb first
+  k_mask_nonpos<<<ew_grid((int64_t)d.B * E), 256, 0, st>>>(w.d_obs_emb, w.obs_emb, (int64_t)d.B * E);
+  PPB_LAUNCH_CHECK();
+  for (size_t k = 0; k < ph_fin.size(); ++k) {
+    int l = D.obs_final.num_layers - 1 - (int)k;
+    const ppb_linear_desc& L = D.obs_final.layers[l];
+    float* dY = (l == D.obs_final.num_layers - 1) ? w.d_obs_emb : w.d_fin_act[l];
+    k_colsum_gather<<<(L.out_dim + 127) / 128, 128, 0, st>>>(dY, L.out_dim, nullptr, d.B, L.out_dim, grad + L.b_off);
+    rc = run_phase(bl.phases[ph_fin[k]], w.problems, st); if (rc) return rc;
+  }
+  for (size_t k = 0; k < ph_obs.size(); ++k) {
+    int l = max_depth - 1 - (int)k;
+    for (int j = 0; j < D.num_obs; ++j) {
+      const ppb_ff_desc& ff = D.obs_ff[j];
+      if (l >= ff.num_layers) continue;
+      const ppb_linear_desc& L = ff.layers[l];
+      bool last = (l == ff.num_layers - 1);
+      const float* dY = last ? w.d_obs_cat + out_off[j] : w.d_obs_act[j][l];
+      int64_t lddy = last ? E : L.out_dim;
+      k_colsum_gather<<<(L.out_dim + 127) / 128, 128, 0, st>>>(dY, lddy, nullptr, d.B, L.out_dim, grad + L.b_off);
+    }
+    rc = run_phase(bl.phases[ph_obs[k]], w.problems, st); if (rc) return rc;
+  }
+  PPB_LAUNCH_CHECK();
+  return PPB_OK;
+}
+
+}  // extern "C"
+
+// =====================================================================================================
+// batch image decoding, Adam, inference-time entry points, host-buffer training step
+// =====================================================================================================
+namespace {
+
+__global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g,
+                                               float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
+                                               float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                                               float gscale) {
+  // torch.optim.Adam (no amsgrad): g += wd*p; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+  // p -= (lr / bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+  int64_t n4 = n >> 2;
+  float step = lr / bc1;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[q], gg = reinterpret_cast<const float4*>(g)[q];
+    float4 mm = reinterpret_cast<float4*>(m)[q], vv = reinterpret_cast<float4*>(v)[q];
+    float pa[4] = {pp.x, pp.y, pp.z, pp.w}, ga[4] = {gg.x, gg.y, gg.z, gg.w};
+    float ma[4] = {mm.x, mm.y, mm.z, mm.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float gr = ga[j] * gscale + wd * pa[j];
+      ma[j] = b1 * ma[j] + (1.0f - b1) * gr;
+      va[j] = b2 * va[j] + (1.0f - b2) * gr * gr;
+      pa[j] -= step * ma[j] / (sqrtf(va[j]) / bc2_sqrt + eps);
+    }
+    reinterpret_cast<float4*>(p)[q] = make_float4(pa[0], pa[1], pa[2], pa[3]);
+    reinterpret_cast<float4*>(m)[q] = make_float4(ma[0], ma[1], ma[2], ma[3]);
+    reinterpret_cast<float4*>(v)[q] = make_float4(va[0], va[1], va[2], va[3]);
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float gr = g[i] * gscale + wd * p[i];
+    float mi = b1 * m[i] + (1.0f - b1) * gr;
+    float vi = b2 * v[i] + (1.0f - b2) * gr * gr;
+    m[i] = mi; v[i] = vi;
+    p[i] -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  }
+}
+
+// inference-time cell: n particles in lock-step at one address; state updated in place.
+// p_row = step projection + biases + (shared) observation projection, identical for all particles.
+__global__ void __launch_bounds__(256) k_cell_infer(const float* __restrict__ rec, const float* __restrict__ p_row,
+                                                     const float* __restrict__ w_smp_t,
+                                                     const float* __restrict__ smp_emb, float* __restrict__ c,
+                                                     float* __restrict__ h, int64_t n, int H, int S, int first) {
+  int64_t total = n * H;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i = e / H;
+    int j = (int)(e % H);
+    float pre[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      int col = g * H + j;
+      float v = p_row[col];
+      if (!first) {
+        v += rec[i * 4 * H + col];
+        for (int s = 0; s < S; ++s) v = fmaf(smp_emb[i * S + s], w_smp_t[(int64_t)s * 4 * H + col], v);
+      }
+      pre[g] = v;
+    }
+    float ig = 1.0f / (1.0f + expf(-pre[0]));
+    float fg = 1.0f / (1.0f + expf(-pre[1]));
+    float gg = tanhf(pre[2]);
+    float og = 1.0f / (1.0f + expf(-pre[3]));
+    float cp = first ? 0.0f : c[i * H + j];
+    float cn = fg * cp + ig * gg;
+    c[i * H + j] = cn;
+    h[i * H + j] = og * tanhf(cn);
+  }
+}
+
+__global__ void k_smp_embed_infer(const float* __restrict__ arena, ppb_addr_desc a, const float* __restrict__ value,
+                                  int64_t n, int S, float* __restrict__ smp_emb) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n * S; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i = e / S;
+    int j = (int)(e % S);
+    float x = value[i];
+    const float* W = arena + a.smp_w_off + (int64_t)j * a.smp_in;
+    float pre = arena[a.smp_b_off + j];
+    if (a.family == PPB_FAMILY_CATEGORICAL) {
+      int cidx = (int)x;
+      if (cidx >= 0 && cidx < a.smp_in) pre += W[cidx];
+    } else {
+      pre += W[0] * x;
+    }
+    smp_emb[e] = fmaxf(pre, 0.0f);
+  }
+}
+
+__global__ void k_step_row_infer(const float* __restrict__ arena, ppb_addr_desc prev, int has_prev, ppb_addr_desc cur,
+                                 const int64_t* __restrict__ type_off, int td, int ad, float* __restrict__ row) {
+  int C2 = 2 * (td + ad);
+  for (int j = threadIdx.x; j < C2; j += blockDim.x) {
+    bool is_prev = j < td + ad;
+    int jj = is_prev ? j : j - (td + ad);
+    float v = 0.0f;
+    if (!is_prev || has_prev) {
+      const ppb_addr_desc& a = is_prev ? prev : cur;
+      v = jj < td ? arena[type_off[a.type_id] + jj] : arena[a.addr_emb_off + (jj - td)];
+    }
+    row[j] = v;
+  }
+}
+
+// raw head output -> distribution parameters as the reference's proposal layers return them
+__global__ void __launch_bounds__(128) k_head_params(const float* __restrict__ out_raw, int out_pad, ppb_addr_desc a,
+                                                      int K, const float* __restrict__ prior0, int s0,
+                                                      const float* __restrict__ prior1, int s1,
+                                                      float* __restrict__ params, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float* x = out_raw + i * out_pad;
+    if (a.family == PPB_FAMILY_CATEGORICAL) {
+      float xs[heads::CMAX], q[heads::CMAX];
+      for (int c = 0; c < a.num_categories; ++c) xs[c] = x[c];
+      heads::categorical_probs(xs, a.num_categories, q);
+      for (int c = 0; c < a.num_categories; ++c) params[i * a.num_categories + c] = q[c];
+    } else {
+      float xs[3 * heads::KMAX], mean[heads::KMAX], sd[heads::KMAX], pr[heads::KMAX], lo, hi;
+      for (int j = 0; j < 3 * K; ++j) xs[j] = x[j];
+      float p0 = prior0 ? prior0[i * s0] : 0.0f, p1 = prior1 ? prior1[i * s1] : 0.0f;
+      heads::mixture_params(a.family, xs, K, p0, p1, mean, sd, pr, &lo, &hi);
+      for (int k = 0; k < K; ++k) {
+        params[i * 3 * K + k] = mean[k];
+        params[i * 3 * K + K + k] = sd[k];
+        params[i * 3 * K + 2 * K + k] = pr[k];
+      }
+    }
+  }
+}
+
+struct InferWs {
+  float *gates, *hid, *out_raw, *smp_emb, *p_row, *emb_row, *w_smp_t;
+  float* obs_act[PPB_MAX_OBS][PPB_MAX_FF_LAYERS];
+  float* obs_cat;
+  float* fin_act[PPB_MAX_FF_LAYERS];
+  Problem* problems;
+  int64_t max_problems, total_bytes;
+};
+
+InferWs carve_infer(const ppb_net* net, int64_t n, void* base) {
+  const ppb_net_desc& D = net->desc;
+  InferWs w;
+  memset(&w, 0, sizeof(w));
+  char* p = (char*)base;
+  int64_t off = 0;
+  auto take = [&](int64_t floats) { float* r = (float*)(p + off); off += align_up(floats * 4, 256); return r; };
+  const int H4 = 4 * D.lstm_dim;
+  w.gates = take(n * H4);
+  w.hid = take(n * net->dh_pad);
+  w.out_raw = take(n * net->out_pad);
+  w.smp_emb = take(n * D.sample_dim);
+  w.p_row = take(H4);
+  w.emb_row = take(2 * (D.type_dim + D.addr_dim));
+  w.w_smp_t = take((int64_t)D.sample_dim * H4);
+  for (int j = 0; j < D.num_obs; ++j)
+    for (int l = 0; l + 1 < D.obs_ff[j].num_layers; ++l) w.obs_act[j][l] = take(n * D.obs_ff[j].layers[l].out_dim);
+  w.obs_cat = take(n * D.obs_dim);
+  for (int l = 0; l + 1 < D.obs_final.num_layers; ++l) w.fin_act[l] = take(n * D.obs_final.layers[l].out_dim);
+  w.max_problems = 64 + 2LL * PPB_MAX_OBS * PPB_MAX_FF_LAYERS;
+  w.problems = (Problem*)take(w.max_problems * (int64_t)(sizeof(Problem) / 4));
+  w.total_bytes = off;
+  return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t ppb_sizeof(int which) {
+  switch (which) {
+    case 0: return sizeof(ppb_net_desc);
+    case 1: return sizeof(ppb_addr_desc);
+    case 2: return sizeof(ppb_batch);
+    case 3: return sizeof(ppb_ff_desc);
+    case 4: return sizeof(ppb_linear_desc);
+    default: return -1;
+  }
+}
+
+int ppb_batch_from_image(const void* image_host, const void* image_dev, int64_t image_bytes, ppb_batch* out) {
+  PPB_CHECK_ARG(image_host && out, "null image");
+  const int64_t* hd = (const int64_t*)image_host;
+  PPB_CHECK_ARG(image_bytes >= (int64_t)(PPB_IMAGE_HEADER_WORDS * 8), "image too small");
+  PPB_CHECK_ARG(hd[0] == PPB_IMAGE_MAGIC, "bad batch image magic");
+  PPB_CHECK_ARG(hd[8] == image_bytes, "image size mismatch");
+  memset(out, 0, sizeof(*out));
+  out->n_traces = (int32_t)hd[1]; out->n_sub = (int32_t)hd[2]; out->t_max = (int32_t)hd[3];
+  out->n_rows = (int32_t)hd[4]; out->n_steps = (int32_t)hd[5]; out->n_groups = (int32_t)hd[6];
+  out->obs_in_total = (int32_t)hd[7];
+  for (int k = 9; k < 9 + 15; ++k)
+    PPB_CHECK_ARG(hd[k] >= PPB_IMAGE_HEADER_WORDS * 8 && hd[k] < image_bytes && (hd[k] & 15) == 0, "bad array offset");
+  const char* Hh = (const char*)image_host;
+  const char* Dv = (const char*)image_dev;
+  out->row_off_host = (const int32_t*)(Hh + hd[9]);
+  out->group_addr_host = (const int32_t*)(Hh + hd[10]);
+  out->group_start_host = (const int32_t*)(Hh + hd[11]);
+  if (Dv) {
+    out->trace_sub = (const int32_t*)(Dv + hd[12]);
+    out->step_addr = (const int32_t*)(Dv + hd[13]);
+    out->step_prev_addr = (const int32_t*)(Dv + hd[14]);
+    out->step_row0 = (const int32_t*)(Dv + hd[15]);
+    out->step_nrows = (const int32_t*)(Dv + hd[16]);
+    out->row_step = (const int32_t*)(Dv + hd[17]);
+    out->row_prev = (const int32_t*)(Dv + hd[18]);
+    out->values = (const float*)(Dv + hd[19]);
+    out->prior0 = (const float*)(Dv + hd[20]);
+    out->prior1 = (const float*)(Dv + hd[21]);
+    out->obs = (const float*)(Dv + hd[22]);
+    out->head_rows = (const int32_t*)(Dv + hd[23]);
+  }
+  return PPB_OK;
+}
+
+int ppb_adam_step(float* arena, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int64_t step, float grad_scale, void* stream) {
+  PPB_CHECK_ARG(arena && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "bad arguments");
+  double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  k_adam<<<ppb_grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(arena, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+                                                                   eps, weight_decay, (float)bc1, (float)sqrt(bc2),
+                                                                   grad_scale);
+  PPB_LAUNCH_CHECK();
+  return PPB_OK;
+}
+
+int64_t ppb_ic_infer_workspace_bytes(const ppb_net* net, int64_t n) {
+  if (!net || n <= 0) return -1;
+  return carve_infer(net, n, nullptr).total_bytes + 1024;
+}
+
+int ppb_ic_embed_observe(ppb_net* net, const float* arena, const float* obs, float* obs_emb_out, int64_t n,
+                         void* workspace, int64_t workspace_bytes, void* stream) {
+  PPB_CHECK_ARG(net && arena && obs && obs_emb_out && workspace && n > 0, "bad arguments");
+  PPB_CHECK_ARG(workspace_bytes >= ppb_ic_infer_workspace_bytes(net, n), "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  InferWs w = carve_infer(net, n, workspace);
+  Builder bl;
+  add_obs_embed(bl, net->desc, arena, obs, (int)n, w.obs_act, w.obs_cat, w.fin_act, obs_emb_out);
+  int rc = upload_and_get(net, bl, w.problems, w.max_problems, st);
+  if (rc) return rc;
+  for (auto& ph : bl.phases) { rc = run_phase(ph, w.problems, st); if (rc) return rc; }
+  return PPB_OK;
+}
+
+int ppb_ic_infer_step(ppb_net* net, const float* arena, const float* obs_emb, int obs_emb_row_stride, int32_t prev_addr,
+                      const float* prev_value, int32_t cur_addr, const float* prior0, int prior0_stride,
+                      const float* prior1, int prior1_stride, float* h, float* c, float* params_out, int64_t n,
+                      void* workspace, int64_t workspace_bytes, int precision, void* stream) {
+  PPB_CHECK_ARG(net && arena && obs_emb && h && c && params_out && workspace && n > 0, "bad arguments");
+  PPB_CHECK_ARG(cur_addr >= 0 && cur_addr < (int)net->addrs.size(), "unknown current address");
+  PPB_CHECK_ARG(prev_addr < (int)net->addrs.size(), "unknown previous address");
+  PPB_CHECK_ARG(prev_addr < 0 || prev_value, "previous value missing");
+  PPB_CHECK_ARG(workspace_bytes >= ppb_ic_infer_workspace_bytes(net, n), "workspace too small");
+  if (obs_emb_row_stride != 0) {
+    ppb_set_error("ppb_ic_infer_step: per-particle observation embeddings are not supported yet (stride must be 0)");
+    return PPB_ENOTSUP;
+  }
+  (void)precision;
+  const ppb_net_desc& D = net->desc;
+  cudaStream_t st = (cudaStream_t)stream;
+  InferWs w = carve_infer(net, n, workspace);
+  const int H = D.lstm_dim, H4 = 4 * H, E = D.obs_dim, S = D.sample_dim, I = net->I, C2 = 2 * (D.type_dim + D.addr_dim);
+  const ppb_addr_desc cur = net->addrs[cur_addr];
+  const bool first = prev_addr < 0;
+  const ppb_addr_desc prev = first ? cur : net->addrs[prev_addr];
+
+  Builder bl;
+  bl.begin();  // 0: p_row = step_emb W_ih[:, E+S:]^T + b_ih
+  bl.add(linear_fwd(w.emb_row, C2, arena + D.w_ih_off + E + S, I, arena + D.b_ih_off, w.p_row, H4, 1, H4, C2, 0));
+  bl.begin();  // 1: p_row += obs_emb W_ih[:, :E]^T + b_hh   (one shared observation row)
+  bl.add(linear_fwd(obs_emb, E, arena + D.w_ih_off, I, arena + D.b_hh_off, w.p_row, H4, 1, H4, E, gemm::kAccumulate));
+  bl.begin();  // 2: recurrent part
+  if (!first) bl.add(linear_fwd(h, H, arena + D.w_hh_off, H, nullptr, w.gates, H4, (int)n, H4, H, 0));
+  bl.begin();  // 3, 4: head (after the cell update)
+  bl.add(linear_fwd(h, H, arena + cur.w1_off, H, arena + cur.b1_off, w.hid, net->dh_pad, (int)n, cur.head_hidden, H, gemm::kRelu));
+  bl.begin();
+  bl.add(linear_fwd(w.hid, net->dh_pad, arena + cur.w2_off, cur.head_hidden, arena + cur.b2_off, w.out_raw, net->out_pad,
+                    (int)n, cur.head_out, cur.head_hidden, 0));
+  int rc = upload_and_get(net, bl, w.problems, w.max_problems, st);
+  if (rc) return rc;
+  k_step_row_infer<<<1, 128, 0, st>>>(arena, prev, first ? 0 : 1, cur, net->d_type_off, D.type_dim, D.addr_dim, w.emb_row);
+  PPB_LAUNCH_CHECK();
+  rc = run_phase(bl.phases[0], w.problems, st); if (rc) return rc;
+  rc = run_phase(bl.phases[1], w.problems, st); if (rc) return rc;
+  if (!first) {
+    k_wsmp_transpose<<<ew_grid(S * H4), 256, 0, st>>>(arena + D.w_ih_off, I, E, S, H4, w.w_smp_t);
+    k_smp_embed_infer<<<ew_grid(n * S), 256, 0, st>>>(arena, prev, prev_value, n, S, w.smp_emb);
+    PPB_LAUNCH_CHECK();
+    rc = run_phase(bl.phases[2], w.problems, st); if (rc) return rc;
+  }
+  k_cell_infer<<<ew_grid(n * H), 256, 0, st>>>(w.gates, w.p_row, w.w_smp_t, w.smp_emb, c, h, n, H, S, first ? 1 : 0);
+  PPB_LAUNCH_CHECK();
+  rc = run_phase(bl.phases[3], w.problems, st); if (rc) return rc;
+  rc = run_phase(bl.phases[4], w.problems, st); if (rc) return rc;
+  k_head_params<<<ew_grid(n, 128), 128, 0, st>>>(w.out_raw, net->out_pad, cur, D.mixture_k, prior0, prior0_stride, prior1,
+                                                 prior1_stride, params_out, n);
+  PPB_LAUNCH_CHECK();
+  return PPB_OK;
+}
+
+int ppb_ic_train_step_host(ppb_net* net, float* arena, float* grad_arena, float* exp_avg, float* exp_avg_sq,
+                           int64_t arena_floats, const void* batch_image_host, int64_t batch_image_bytes,
+                           void* batch_image_dev, void* workspace, int64_t workspace_bytes, int precision, float lr,
+                           float beta1, float beta2, float eps, float weight_decay, int64_t step, float* loss_host,
+                           int32_t* status_host, void* stream) {
+  PPB_CHECK_ARG(net && arena && grad_arena && exp_avg && exp_avg_sq && batch_image_host && batch_image_dev && workspace,
+                "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  PPB_CUDA(cudaMemcpyAsync(batch_image_dev, batch_image_host, batch_image_bytes, cudaMemcpyHostToDevice, st));
+  ppb_batch b;
+  int rc = ppb_batch_from_image(batch_image_host, batch_image_dev, batch_image_bytes, &b);
+  if (rc) return rc;
+  Dims d = dims_of(&b);
+  int64_t need = ppb_ic_workspace_bytes(net, d.B, d.R, d.T, d.NS, d.G);
+  PPB_CHECK_ARG(workspace_bytes >= need + 256, "workspace too small (need ppb_ic_workspace_bytes + 256)");
+  float* loss_dev = (float*)((char*)workspace + need);  // loss scalar + status live after the carved region
+  int32_t* status_dev = (int32_t*)(loss_dev + 1);
+  PPB_CUDA(cudaMemsetAsync(grad_arena, 0, arena_floats * sizeof(float), st));
+  rc = ppb_ic_loss_forward(net, arena, &b, workspace, need, precision, loss_dev, status_dev, nullptr, 1, stream);
+  if (rc) return rc;
+  rc = ppb_ic_loss_backward(net, arena, grad_arena, &b, workspace, need, precision, 1.0f, stream);
+  if (rc) return rc;
+  rc = ppb_adam_step(arena, grad_arena, exp_avg, exp_avg_sq, arena_floats, lr, beta1, beta2, eps, weight_decay, step, 1.0f,
+                     stream);
+  if (rc) return rc;
+  if (loss_host) PPB_CUDA(cudaMemcpyAsync(loss_host, loss_dev, sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (status_host) PPB_CUDA(cudaMemcpyAsync(status_host, status_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  PPB_CUDA(cudaStreamSynchronize(st));
+  return PPB_OK;
+}
+
+}  // extern "C"

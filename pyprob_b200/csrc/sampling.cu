@@ -173,6 +173,7 @@ extern "C" {
 
 int ppb_normal_sample(const float* mean, int mean_stride, const float* stddev, int stddev_stride, float* value_out,
                       float* lp_out, int64_t n, uint64_t seed, uint64_t offset, int64_t first_index, void* stream) {
+  if (n == 0) return PPB_OK;
   PPB_CHECK_ARG(n >= 0 && mean && stddev && value_out, "bad arguments");
   if (n == 0) return PPB_OK;
   k_normal<<<ppb_grid_for(n, kThreads, 1), kThreads, 0, (cudaStream_t)stream>>>(
@@ -183,6 +184,7 @@ int ppb_normal_sample(const float* mean, int mean_stride, const float* stddev, i
 
 int ppb_uniform_sample(const float* low, int low_stride, const float* high, int high_stride, float* value_out,
                        float* lp_out, int64_t n, uint64_t seed, uint64_t offset, int64_t first_index, void* stream) {
+  if (n == 0) return PPB_OK;
   PPB_CHECK_ARG(n >= 0 && low && high && value_out, "bad arguments");
   if (n == 0) return PPB_OK;
   k_uniform<<<ppb_grid_for(n, kThreads, 1), kThreads, 0, (cudaStream_t)stream>>>(
@@ -193,6 +195,7 @@ int ppb_uniform_sample(const float* low, int low_stride, const float* high, int 
 
 int ppb_poisson_sample(const float* rate, int rate_stride, float* value_out, float* lp_out, int64_t n, uint64_t seed,
                        uint64_t offset, int64_t first_index, void* stream) {
+  if (n == 0) return PPB_OK;
   PPB_CHECK_ARG(n >= 0 && rate && value_out, "bad arguments");
   if (n == 0) return PPB_OK;
   k_poisson<<<ppb_grid_for(n, kThreads, 1), kThreads, 0, (cudaStream_t)stream>>>(P{rate, rate_stride}, value_out,
@@ -204,6 +207,7 @@ int ppb_poisson_sample(const float* rate, int rate_stride, float* value_out, flo
 int ppb_categorical_sample(const float* probs, int64_t probs_row_stride, int num_categories, float* value_out,
                            float* lp_out, int64_t n, uint64_t seed, uint64_t offset, int64_t first_index,
                            void* stream) {
+  if (n == 0) return PPB_OK;
   PPB_CHECK_ARG(n >= 0 && probs && value_out && num_categories > 0, "bad arguments");
   if (n == 0) return PPB_OK;
   k_categorical<<<ppb_grid_for(n, kThreads, 1), kThreads, 0, (cudaStream_t)stream>>>(
@@ -215,6 +219,7 @@ int ppb_categorical_sample(const float* probs, int64_t probs_row_stride, int num
 int ppb_mixture_normal_sample(const float* means, const float* stddevs, const float* probs, int64_t row_stride, int K,
                               float* value_out, float* lp_out, int64_t n, uint64_t seed, uint64_t offset,
                               int64_t first_index, void* stream) {
+  if (n == 0) return PPB_OK;
   PPB_CHECK_ARG(n >= 0 && means && stddevs && probs && value_out && K > 0 && K <= 32, "bad arguments (K<=32)");
   if (n == 0) return PPB_OK;
   k_mixture<false><<<ppb_grid_for(n, kThreads, 1), kThreads, 0, (cudaStream_t)stream>>>(
@@ -228,6 +233,7 @@ int ppb_mixture_truncated_normal_sample(const float* means, const float* stddevs
                                         int64_t row_stride, int K, const float* low, int low_stride,
                                         const float* high, int high_stride, float* value_out, float* lp_out,
                                         int64_t n, uint64_t seed, uint64_t offset, int64_t first_index, void* stream) {
+  if (n == 0) return PPB_OK;
   PPB_CHECK_ARG(n >= 0 && means && stddevs && probs && low && high && value_out && K > 0 && K <= 32,
                 "bad arguments (K<=32)");
   if (n == 0) return PPB_OK;

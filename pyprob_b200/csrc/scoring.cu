@@ -218,6 +218,7 @@ extern "C" {
 
 int ppb_normal_log_prob(const float* value, const float* mean, int mean_stride, const float* stddev,
                         int stddev_stride, float* lp_out, double* acc, double acc_scale, int64_t n, void* stream) {
+  if (n == 0) return PPB_OK;
   PPB_CHECK_ARG(n >= 0 && value && mean && stddev, "null pointer or negative n");
   PPB_CHECK_ARG((mean_stride | 1) == 1 && (stddev_stride | 1) == 1, "strides must be 0 or 1");
   return launch_score2(value, Param{mean, mean_stride}, Param{stddev, stddev_stride}, Sink{lp_out, acc, acc_scale}, n,
@@ -226,6 +227,7 @@ int ppb_normal_log_prob(const float* value, const float* mean, int mean_stride, 
 
 int ppb_uniform_log_prob(const float* value, const float* low, int low_stride, const float* high, int high_stride,
                          float* lp_out, double* acc, double acc_scale, int64_t n, void* stream) {
+  if (n == 0) return PPB_OK;
   PPB_CHECK_ARG(n >= 0 && value && low && high, "null pointer or negative n");
   PPB_CHECK_ARG((low_stride | 1) == 1 && (high_stride | 1) == 1, "strides must be 0 or 1");
   return launch_score2(value, Param{low, low_stride}, Param{high, high_stride}, Sink{lp_out, acc, acc_scale}, n, stream,
@@ -234,6 +236,7 @@ int ppb_uniform_log_prob(const float* value, const float* low, int low_stride, c
 
 int ppb_poisson_log_prob(const float* value, const float* rate, int rate_stride, float* lp_out, double* acc,
                          double acc_scale, int64_t n, void* stream) {
+  if (n == 0) return PPB_OK;
   PPB_CHECK_ARG(n >= 0 && value && rate, "null pointer or negative n");
   PPB_CHECK_ARG((rate_stride | 1) == 1, "strides must be 0 or 1");
   return launch_score2(value, Param{rate, rate_stride}, Param{rate, 0}, Sink{lp_out, acc, acc_scale}, n, stream,
@@ -242,6 +245,7 @@ int ppb_poisson_log_prob(const float* value, const float* rate, int rate_stride,
 
 int ppb_categorical_log_prob(const float* value, const float* probs, int64_t probs_row_stride, int num_categories,
                              float* lp_out, double* acc, double acc_scale, int64_t n, void* stream) {
+  if (n == 0) return PPB_OK;
   PPB_CHECK_ARG(n >= 0 && value && probs && num_categories > 0, "bad arguments");
   PPB_CHECK_ARG(probs_row_stride == 0 || probs_row_stride >= num_categories, "row stride < num_categories");
   if (n == 0) return PPB_OK;
@@ -255,6 +259,7 @@ int ppb_categorical_log_prob(const float* value, const float* probs, int64_t pro
 int ppb_mixture_normal_log_prob(const float* value, const float* means, const float* stddevs, const float* probs,
                                 int64_t row_stride, int K, float* lp_out, double* acc, double acc_scale, int64_t n,
                                 void* stream) {
+  if (n == 0) return PPB_OK;
   PPB_CHECK_ARG(n >= 0 && value && means && stddevs && probs && K > 0, "bad arguments");
   return launch_mixture<false>(value, means, stddevs, probs, row_stride, K, Param{nullptr, 0}, Param{nullptr, 0},
                                Sink{lp_out, acc, acc_scale}, n, stream);
@@ -264,6 +269,7 @@ int ppb_mixture_truncated_normal_log_prob(const float* value, const float* means
                                           const float* probs, int64_t row_stride, int K, const float* low,
                                           int low_stride, const float* high, int high_stride, float* lp_out,
                                           double* acc, double acc_scale, int64_t n, void* stream) {
+  if (n == 0) return PPB_OK;
   PPB_CHECK_ARG(n >= 0 && value && means && stddevs && probs && low && high && K > 0, "bad arguments");
   return launch_mixture<true>(value, means, stddevs, probs, row_stride, K, Param{low, low_stride},
                               Param{high, high_stride}, Sink{lp_out, acc, acc_scale}, n, stream);

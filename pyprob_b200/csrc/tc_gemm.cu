@@ -35,6 +35,12 @@ __global__ void __launch_bounds__(256) k_pack(const float* __restrict__ X, int64
 constexpr int kStages = 3;
 constexpr int kGemmThreads = 192;
 constexpr int kBN = 128;
+// The tensor core adds each MMA result into the fp32 TMEM accumulator with truncation (measured: error
+// grows linearly with the number of accumulating instructions, ~0.4 ulp each, biased toward zero).  To stay
+// fp32-faithful the 3xTF32 path therefore spreads the work over three accumulators that the epilogue
+// sums with round-to-nearest adds: hi*hi of even k-blocks, hi*hi of odd k-blocks, and the two small
+// cross terms (lo*hi + hi*lo, 2^-11 of the main magnitude).
+constexpr int kTmemCols = 512;
 struct __align__(1024) GemmSmem {
   float a_hi[kStages][kTileFloats];
   float a_lo[kStages][kTileFloats];
@@ -62,7 +68,7 @@ k_gemm_packed(const float* __restrict__ A_hi, const float* __restrict__ A_lo, co
     mbar_init(&sm.tmem_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<kBN>(&sm.tmem_base);
+  if (warp == 1) tmem_alloc<kTmemCols>(&sm.tmem_base);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -98,13 +104,14 @@ k_gemm_packed(const float* __restrict__ A_hi, const float* __restrict__ A_lo, co
 #pragma unroll
         for (int k = 0; k < kTileK / 8; ++k) {
           uint64_t adv = (uint64_t)(k * 8 * 4 >> 4);  // 32 bytes per UMMA_K step, encoded >> 4
-          uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
           if (X3) {
-            mma_tf32(tmem, al + adv, bh + adv, idesc, first);
-            mma_tf32(tmem, ah + adv, bl + adv, idesc, 1u);
-            mma_tf32(tmem, ah + adv, bh + adv, idesc, 1u);
+            uint32_t first_lo = (kb == 0 && k == 0) ? 0u : 1u;
+            uint32_t first_hi = (kb < 2 && k == 0) ? 0u : 1u;  // even / odd k-blocks own separate accumulators
+            mma_tf32(tmem + 2 * kBN, al + adv, bh + adv, idesc, first_lo);
+            mma_tf32(tmem + 2 * kBN, ah + adv, bl + adv, idesc, 1u);
+            mma_tf32(tmem + (kb & 1) * kBN, ah + adv, bh + adv, idesc, first_hi);
           } else {
-            mma_tf32(tmem, ah + adv, bh + adv, idesc, first);
+            mma_tf32(tmem, ah + adv, bh + adv, idesc, (kb == 0 && k == 0) ? 0u : 1u);
           }
         }
         mma_commit(&sm.empty[s]);  // frees the stage once these MMAs have read it
@@ -121,6 +128,17 @@ k_gemm_packed(const float* __restrict__ A_hi, const float* __restrict__ A_lo, co
     for (int cb = 0; cb < kBN / 32; ++cb) {
       float v[32];
       tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + cb * 32, v);
+      if (X3) {
+        float u[32];
+        if (KB > 1) {
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + kBN + cb * 32, u);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += u[j];
+        }
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 2 * kBN + cb * 32, u);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += u[j];
+      }
       int col0 = nt * kBN + cb * 32;
       if (row < M) {
 #pragma unroll
@@ -139,7 +157,7 @@ k_gemm_packed(const float* __restrict__ A_hi, const float* __restrict__ A_lo, co
   __syncthreads();
   if (warp == 1) {
     fence_after_sync();
-    tmem_dealloc<kBN>(tmem);
+    tmem_dealloc<kTmemCols>(tmem);
   }
 }
 

@@ -65,6 +65,9 @@ def poisson_log_prob(value, rate, lp_out=None, acc=None, acc_scale=1.0):
 
 def _rows(t, n, device):
     """[C] shared or [n, C] per particle -> (tensor, row_stride, C)"""
+    if torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1 \
+            and t.size(0) == n and t.stride(0) >= t.size(1):
+        return t, t.stride(0), t.size(1)  # strided rows (e.g. a column block of the head output): no copy
     t = _f32(t, device)
     if t.dim() == 1:
         return t, 0, t.size(0)

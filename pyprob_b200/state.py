@@ -1,0 +1,301 @@
+"""Lock-step trace interpreter: ``sample`` / ``observe`` / ``tag`` / ``factor`` over n particles at once.
+
+Per-site weight semantics follow the reference's IS and IC branches (pyprob/state.py:118-155, :192-219,
+:280-288); the per-particle Python loop of pyprob/model.py:59-60 is replaced by one execution of the user's
+``forward`` in which every sampled value is a length-n CUDA tensor.  Data-dependent control flow is written
+with :func:`while_loop` (lanes leave the loop individually); a model that instead calls ``float()`` on a
+sampled tensor still works — the engine falls back to one particle per execution (see model.py).
+"""
+import dis
+import sys
+import time
+
+import torch
+
+from . import util
+from .distributions import Categorical, Distribution, Mixture, Normal, Poisson, Uniform
+from .trace import BatchedTrace, Site
+from .util import InferenceEngine, PriorInflation, TraceMode
+
+_trace_mode = TraceMode.PRIOR
+_inference_engine = InferenceEngine.IMPORTANCE_SAMPLING
+_prior_inflation = PriorInflation.DISABLED
+_likelihood_importance = 1.0
+_current_trace = None
+_root_function_name = None
+_network = None
+_previous_site = None
+_observed = {}
+_mask = None            # bool [n] of lanes executing the current statement, None = all
+_trace_start = None
+_target_cache = {}
+
+
+# ---- addressing (same information content as the reference's bytecode addresses, state.py:31-84) --------
+def _assignment_target(code, lasti):
+    key = (code, lasti)
+    if key not in _target_cache:
+        target = None
+        for ins in dis.get_instructions(code):
+            if ins.offset <= lasti or ins.opname in ('CACHE', 'PRECALL', 'NOP'):
+                continue
+            if ins.opname in ('STORE_FAST', 'STORE_NAME', 'STORE_GLOBAL', 'STORE_DEREF'):
+                target = ins.argval
+            elif ins.opname in ('RETURN_VALUE',):
+                target = 'return'
+            break
+        _target_cache[key] = target
+    return _target_cache[key]
+
+
+def _extract_address(depth=2):
+    frame = sys._getframe(depth)
+    ip = frame.f_lasti
+    target = _assignment_target(frame.f_code, ip)
+    names = []
+    f = frame
+    while f is not None:
+        n = f.f_code.co_name
+        if n.startswith('<') and n != '<listcomp>':
+            break
+        names.append(n)
+        if n == _root_function_name:
+            break
+        f = f.f_back
+    return '{}__{}__{}'.format(ip, '__'.join(reversed(names)), target if target is not None else '?')
+
+
+def _addresses(distribution, address, depth):
+    base = (_extract_address(depth + 1) if address is None else address) + '__' + distribution._address_suffix
+    instance = _current_trace.next_instance(base)
+    return base, instance, base + '__' + str(instance)
+
+
+# ---- helpers -----------------------------------------------------------------------------------------------
+def _inflate(distribution):
+    if _prior_inflation == PriorInflation.ENABLED:
+        if isinstance(distribution, Categorical):
+            return Categorical(torch.full((distribution.num_categories,), 1.0 / distribution.num_categories))
+        if isinstance(distribution, Normal):
+            return Normal(distribution.loc, distribution.scale * 3)
+    return None
+
+
+def _broadcast_value(value, n):
+    v = torch.as_tensor(value, dtype=torch.float32).to('cuda').reshape(-1)
+    if v.numel() == 1 and n > 1:
+        v = v.expand(n).contiguous()
+    elif v.numel() != n:
+        raise ValueError('pyprob_b200 scores scalar random variables: observed value has {} elements for {} '
+                         'particles'.format(v.numel(), n))
+    return v
+
+
+def _accumulate(trace, fn):
+    """Run fn(acc) (which adds weight terms into acc) for the lanes of the current mask only."""
+    if _mask is None:
+        fn(trace.log_w)
+    else:
+        tmp = trace.log_w.clone()
+        fn(tmp)
+        trace.log_w = torch.where(_mask, tmp, trace.log_w)
+
+
+def _prior_params(distribution):
+    if isinstance(distribution, Normal):
+        return distribution.loc, distribution.scale
+    if isinstance(distribution, Uniform):
+        return distribution.low, distribution.high
+    return None, None
+
+
+# ---- public statements ----------------------------------------------------------------------------------------
+def tag(value, name=None, address=None):
+    if _current_trace is None:
+        return
+    base = (_extract_address(2) if address is None else address) + '__None'
+    instance = _current_trace.next_instance(base)
+    _current_trace.add(Site(None, value, base, base + '__' + str(instance), instance, name=name, tagged=True,
+                            mask=_mask))
+
+
+def factor(log_prob=None, log_prob_func=None, name=None, address=None):
+    """Add an arbitrary per-particle log-weight term (reference: state.py:113-115, distributions/factor.py)."""
+    if _current_trace is None:
+        return
+    lp = log_prob_func() if log_prob is None else log_prob
+    lp = _broadcast_value(lp, _current_trace.n).double() * _likelihood_importance
+    _accumulate(_current_trace, lambda acc: acc.add_(lp))
+
+
+def observe(distribution, value=None, name=None, address=None):
+    trace = _current_trace
+    if trace is None:
+        return
+    base, instance, addr = _addresses(distribution, address, 2)
+    n = trace.n
+    if name in _observed:
+        value = _broadcast_value(_observed[name], n)
+    elif value is not None:
+        value = _broadcast_value(value, n)
+    elif _trace_mode == TraceMode.PRIOR_FOR_INFERENCE_NETWORK:
+        value = distribution.sample(n)
+    if value is None:
+        trace.add(Site(distribution, None, base, addr, instance, name=name, observed=False, mask=_mask))
+        return None
+    if _trace_mode == TraceMode.POSTERIOR:
+        _accumulate(trace, lambda acc: distribution.score_into(value, acc, _likelihood_importance))
+    trace.add(Site(distribution, value, base, addr, instance, name=name, observed=True, mask=_mask))
+    return value
+
+
+def sample(distribution, name=None, address=None, control=True):
+    global _previous_site
+    trace = _current_trace
+    if trace is None:
+        return distribution.sample()
+    base, instance, addr = _addresses(distribution, address, 2)
+    n = trace.n
+    if name in _observed:
+        value = _broadcast_value(_observed[name], n)
+        if _trace_mode == TraceMode.POSTERIOR:
+            _accumulate(trace, lambda acc: distribution.score_into(value, acc, _likelihood_importance))
+        trace.add(Site(distribution, value, base, addr, instance, name=name, observed=True, mask=_mask))
+        return value
+
+    use_network = (_trace_mode == TraceMode.POSTERIOR and control and
+                   _inference_engine == InferenceEngine.IMPORTANCE_SAMPLING_WITH_INFERENCE_NETWORK)
+    if use_network:
+        value = _sample_from_proposal(trace, distribution, addr, n)
+    else:
+        inflated = _inflate(distribution)
+        if inflated is None:
+            value = distribution.sample(n)       # proposal == prior: weight term is exactly zero (state.py:198)
+        else:
+            value, q_lp = inflated.sample(n, with_log_prob=True)
+            if _trace_mode == TraceMode.POSTERIOR or _trace_mode == TraceMode.PRIOR_FOR_INFERENCE_NETWORK:
+                def fn(acc):
+                    distribution.score_into(value, acc, 1.0)
+                    acc.sub_(q_lp.double())
+                _accumulate(trace, fn)
+    site = Site(distribution, value, base, addr, instance, control=control, name=name, mask=_mask)
+    trace.add(site)
+    if use_network:
+        _previous_site = site
+    return value
+
+
+def _sample_from_proposal(trace, distribution, addr, n):
+    """IC branch (state.py:203-219): value ~ q(.|LSTM state); weight += log p(value) - log q(value)."""
+    net = _network
+    prev = _previous_site
+    p0, p1 = _prior_params(distribution)
+    keep = None
+    if _mask is not None and net._infer_state is not None:
+        keep = (net._infer_state[0].clone(), net._infer_state[1].clone())
+    params = net._infer_step_batched(addr, None if prev is None else prev.address,
+                                     None if prev is None else prev.value, p0, p1, n)
+    if params is None:
+        return distribution.sample(n)  # unknown address: propose from the prior, weight term zero
+    if keep is not None:  # lanes outside the mask keep their LSTM state
+        h, c = net._infer_state
+        m = _mask.view(-1, 1)
+        h.copy_(torch.where(m, h, keep[0]))
+        c.copy_(torch.where(m, c, keep[1]))
+    K = net._proposal_mixture_components
+    if isinstance(distribution, Categorical):
+        proposal = Categorical(probs=params)
+    elif isinstance(distribution, Normal):
+        proposal = Mixture.from_rows(params[:, :K], params[:, K:2 * K], params[:, 2 * K:])
+    elif isinstance(distribution, Uniform):
+        proposal = Mixture.from_rows(params[:, :K], params[:, K:2 * K], params[:, 2 * K:], distribution.low,
+                                     distribution.high)
+    elif isinstance(distribution, Poisson):
+        proposal = Mixture.from_rows(params[:, :K], params[:, K:2 * K], params[:, 2 * K:], 0.0, 40.0)
+    else:
+        raise RuntimeError('Distribution currently unsupported: {}'.format(distribution.name))
+    value, q_lp = proposal.sample(n, with_log_prob=True)
+
+    def fn(acc):
+        distribution.score_into(value, acc, 1.0)
+        acc.sub_(q_lp.double())
+    _accumulate(trace, fn)
+    return value
+
+
+def while_loop(cond_fn, body_fn, state, max_iterations=10000):
+    """Lock-step ``while cond(state): state = body(state)`` over particles.
+
+    ``state`` is a dict of length-n tensors; ``cond_fn(state)`` returns a bool [n]; lanes whose condition is
+    false stop executing sample/observe statements (their trace ends there) while the others continue."""
+    global _mask
+    trace = _current_trace
+    n = trace.n if trace is not None else None
+    outer = _mask
+    state = {k: (v if torch.is_tensor(v) else torch.full((n,), float(v), device='cuda')) for k, v in state.items()}
+    for _ in range(max_iterations):
+        m = cond_fn(state)
+        if outer is not None:
+            m = m & outer
+        if not bool(m.any()):
+            break
+        _mask = m
+        try:
+            out = body_fn(state)
+        finally:
+            _mask = outer
+        state = {k: torch.where(m, out[k].to(state[k].dtype), state[k]) for k in state}
+    else:
+        raise RuntimeError('while_loop: exceeded max_iterations')
+    return state
+
+
+# ---- trace life cycle (reference: state.py:296-354) -------------------------------------------------------------
+def _init_traces(func, trace_mode=TraceMode.PRIOR, prior_inflation=PriorInflation.DISABLED,
+                 inference_engine=InferenceEngine.IMPORTANCE_SAMPLING, inference_network=None, observe=None,
+                 likelihood_importance=1.0):
+    global _trace_mode, _inference_engine, _prior_inflation, _likelihood_importance
+    global _root_function_name, _network, _observed
+    if inference_engine in (InferenceEngine.LIGHTWEIGHT_METROPOLIS_HASTINGS,
+                            InferenceEngine.RANDOM_WALK_METROPOLIS_HASTINGS):
+        raise NotImplementedError('pyprob_b200 implements the importance-sampling engines only (MCMC is sequential '
+                                  'and out of scope; use the reference for LMH/RMH)')
+    _trace_mode, _inference_engine = trace_mode, inference_engine
+    _prior_inflation, _likelihood_importance = prior_inflation, float(likelihood_importance)
+    _root_function_name = func.__code__.co_name
+    if observe is None:
+        _observed = {}
+    else:
+        if any(v is None for v in observe.values()):
+            raise RuntimeError('Observe has missing value(s): {}'.format(observe))
+        _observed = observe
+    _network = inference_network
+    if _network is None:
+        if inference_engine == InferenceEngine.IMPORTANCE_SAMPLING_WITH_INFERENCE_NETWORK:
+            raise ValueError('Cannot run trace with IMPORTANCE_SAMPLING_WITH_INFERENCE_NETWORK without an inference '
+                             'network.')
+    else:
+        _network.eval()
+        _network._infer_init(_observed)
+
+
+def _begin_trace(n):
+    global _current_trace, _previous_site, _trace_start, _mask
+    _trace_start = time.time()
+    _current_trace = BatchedTrace(n)
+    _previous_site = None
+    _mask = None
+    if _network is not None:
+        _network._infer_state = None
+
+
+def _end_trace(result):
+    global _current_trace
+    trace = _current_trace
+    trace.result = result
+    trace.execution_time_sec = time.time() - _trace_start
+    _current_trace = None
+    return trace
+
+
+__all__ = ['sample', 'observe', 'tag', 'factor', 'while_loop', 'Distribution']

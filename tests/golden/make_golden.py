@@ -117,3 +117,108 @@ if __name__ == '__main__':
     fx.update(gum_is_fixture())
     np.savez_compressed(os.path.join(HERE, 'scoring_golden.npz'), **fx)
     print('wrote scoring_golden.npz with', len(fx), 'arrays')
+
+
+# ------------------------------------------------------------------------------------------------------
+# network fixtures: reference InferenceNetworkLSTM._loss + backward on real reference traces
+# ------------------------------------------------------------------------------------------------------
+def _silence():
+    import contextlib
+    import io
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def network_fixture(model, observe_embeddings, lstm_dim, K, batch_size, train_traces, seed, tag):
+    from pyprob import InferenceNetwork as INType
+    from pyprob.nn.dataset import Batch, OnlineDataset
+    sys.path.insert(0, ROOT)
+    from oracle import network as onet
+    pyprob.seed(seed)
+    with _silence():
+        model.learn_inference_network(num_traces=train_traces, batch_size=batch_size, inference_network=INType.LSTM,
+                                      observe_embeddings=observe_embeddings, lstm_dim=lstm_dim,
+                                      proposal_mixture_components=K)
+    net = model._inference_network
+    ds = OnlineDataset(model)
+    traces = [ds[i] for i in range(batch_size)]
+    batch = Batch(traces)
+    with _silence():
+        changed = net._polymorph(batch)
+    net.zero_grad()
+    success, loss = net._loss(batch)
+    assert success
+    loss.backward()
+    fx = {tag + '/loss': np.asarray(float(loss), dtype=np.float64)}
+    names = list(observe_embeddings.keys())
+    in_dims = [int(np.prod(traces[0].named_variables[n].value.shape)) or 1 for n in names]
+    fx[tag + '/observe_names'] = np.asarray(names)
+    fx[tag + '/observe_in_dims'] = np.asarray(in_dims)
+    fx[tag + '/dims'] = np.asarray([lstm_dim, K, batch_size])
+    for k, v in net.state_dict().items():
+        fx[tag + '/param/' + k] = v.detach().numpy()
+    for k, p in net.named_parameters():
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        fx[tag + '/grad/' + k] = g.detach().numpy()
+    # address table in the network's insertion order (= address ids)
+    fx[tag + '/address_order'] = np.asarray(list(net._layers_address_embedding.keys()))
+    fx[tag + '/type_order'] = np.asarray(list(net._layers_distribution_type_embedding.keys()))
+    for s, sub in enumerate(batch.sub_batches):
+        sb = onet.sub_batch_from_traces(sub, names)
+        p = '{}/sub{}/'.format(tag, s)
+        fx[p + 'addresses'] = np.asarray(sb['addresses'])
+        fx[p + 'families'] = np.asarray(sb['families'])
+        fx[p + 'num_categories'] = np.asarray(sb['num_categories'])
+        for k in ('values', 'prior0', 'prior1', 'obs'):
+            fx[p + k] = sb[k].numpy()
+        # per-(t,b) reference log-probs of the proposal, recomputed through the reference layers
+        with torch.no_grad():
+            obs_emb = net._embed_observe(sub)
+    fx[tag + '/num_sub'] = np.asarray(len(batch.sub_batches))
+    return fx
+
+
+def make_network_fixtures():
+    from pyprob import Model
+
+    class GUM(Model):
+        def __init__(self):
+            super().__init__('gum')
+
+        def forward(self):
+            mu = pyprob.sample(Normal(1, math.sqrt(5)))
+            lik = Normal(mu, math.sqrt(2))
+            pyprob.observe(lik, name='obs0')
+            pyprob.observe(lik, name='obs1')
+            return mu
+
+    class Mixed(Model):
+        """All four proposal-head families, data-dependent priors, two trace types (branching)."""
+
+        def __init__(self):
+            super().__init__('mixed')
+
+        def forward(self):
+            u = pyprob.sample(Uniform(-1, 2))
+            k = pyprob.sample(Categorical([0.2, 0.3, 0.5]))
+            if int(k) == 0:
+                z = pyprob.sample(Normal(u, 0.5))
+            else:
+                z = pyprob.sample(Poisson(3.0))
+                z = z * 0.25
+            mu = pyprob.sample(Normal(z * 0.1, 1))
+            pyprob.observe(Normal(mu, 0.3), name='y0')
+            pyprob.observe(Normal(u, 0.7), name='y1')
+            return mu
+
+    pyprob.set_verbosity(0)
+    fx = {}
+    fx.update(network_fixture(GUM(), {'obs0': {'dim': 8}, 'obs1': {'dim': 8}}, lstm_dim=32, K=10, batch_size=16,
+                              train_traces=64, seed=11, tag='gum'))
+    fx.update(network_fixture(Mixed(), {'y0': {'dim': 8, 'depth': 2}, 'y1': {'dim': 4, 'depth': 1}}, lstm_dim=32, K=5,
+                              batch_size=24, train_traces=96, seed=12, tag='mixed'))
+    np.savez_compressed(os.path.join(HERE, 'network_golden.npz'), **fx)
+    print('wrote network_golden.npz with', len(fx), 'arrays')
+
+
+if __name__ == '__main__':
+    make_network_fixtures()

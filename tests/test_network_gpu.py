@@ -1,0 +1,141 @@
+"""GPU parity of the proposal-network training path (C-ABI ppb_ic_loss_forward/backward, ppb_adam_step):
+  (1) against the UNMODIFIED reference's loss and gradients on identical traces/weights (golden fixture),
+  (2) against the oracle on seeded random networks/batches with ragged sub-batches and all four families,
+  (3) size-independent properties at larger sizes (loss additivity over sub-batches, gradient linearity).
+Tolerance: 1e-4 relative on losses / log-probs / gradients (north_star), index tensors exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import network as onet
+from pyprob_b200 import synthetic
+from tests import netfixture
+
+pytestmark = pytest.mark.gpu
+
+
+def _net_from_fixture(fx, precision=0):
+    obs_emb = {}
+    for name in fx['observe_names']:
+        # recover dim/depth from the parameter shapes
+        depth = sum(1 for k in fx['params'] if k.startswith('_layers_observe_embedding.{}.'.format(name)) and k.endswith('weight'))
+        dim = fx['params']['_layers_observe_embedding.{}._layers.{}.weight'.format(name, depth - 1)].shape[0]
+        obs_emb[name] = {'dim': int(dim), 'depth': depth}
+    fam_of = {}
+    for sb in fx['subs']:
+        for a, f, c in zip(sb['addresses'], sb['families'], sb['num_categories']):
+            fam_of[a] = (f, c)
+    # create types in the reference's insertion order so that type ids agree
+    addresses = [(a, fam_of[a][0], fam_of[a][1]) for a in fx['address_order']]
+    net = synthetic.build_network(obs_emb, fx['observe_in_dims'], addresses, lstm_dim=fx['lstm_dim'],
+                                  mixture_components=fx['K'], precision=precision)
+    net.load_reference_state_dict(fx['params'])
+    return net
+
+
+def _subs_numpy(subs):
+    return [{k: (v.numpy() if torch.is_tensor(v) else v) for k, v in sb.items()} for sb in subs]
+
+
+def _check_grads(net, want, rtol=1e-4):
+    for k, g in want.items():
+        got = net.grad_view(k).cpu()
+        scale = max(float(g.abs().max()), 1e-6)
+        err = float((got - g).abs().max())
+        assert err <= rtol * scale + 1e-7, (k, err, scale)
+
+
+@pytest.mark.parametrize('tag', ['gum', 'mixed'])
+@pytest.mark.parametrize('precision', [2])
+def test_loss_and_grads_vs_reference_fixture(cuda, tag, precision):
+    fx = netfixture.load(tag)
+    net = _net_from_fixture(fx, precision)
+    batch = synthetic.ArrayBatch(_subs_numpy(fx['subs']))
+    success, loss = net._loss(batch)
+    assert success
+    assert abs(float(loss) - fx['loss']) <= 1e-4 * abs(fx['loss'])
+    loss.backward()
+    _check_grads(net, fx['grads'])
+
+
+def test_row_log_probs_vs_oracle(cuda):
+    fx = netfixture.load('mixed')
+    net = _net_from_fixture(fx)
+    batch = synthetic.ArrayBatch(_subs_numpy(fx['subs']))
+    enc, lp = net.row_log_probs(batch)
+    lp = lp.cpu().numpy()
+    _, _, ref = onet.loss_and_grads(fx['params'], fx['subs'], fx['observe_names'], fx['observe_in_dims'], fx['K'])
+    a = enc.arrays
+    for pos, s in enumerate(enc.sub_order):
+        T, B = ref[s].shape
+        for t in range(T):
+            st = [i for i in range(enc.n_steps) if a['step_row0'][i] == a['row_off'][t] + enc.trace_off[pos]][0]
+            r0 = a['step_row0'][st]
+            np.testing.assert_allclose(lp[r0:r0 + B], ref[s][t].numpy(), rtol=1e-4, atol=1e-5)
+
+
+def _random_case(seed, lstm_dim, K, spec):
+    rng = np.random.default_rng(seed)
+    table = [('a_u', 'Uniform', 0), ('a_c', 'Categorical', 5), ('a_n', 'Normal', 0), ('a_p', 'Poisson', 0),
+             ('a_n2', 'Normal', 0), ('a_c2', 'Categorical', 3)]
+    net = synthetic.build_network({'o0': {'dim': 12, 'depth': 2}, 'o1': {'dim': 6, 'depth': 3}}, [3, 1], table,
+                                  lstm_dim=lstm_dim, mixture_components=K, seed=seed)
+    subs = [synthetic.random_sub_batch(rng, [table[i] for i in seq], B, 4) for seq, B in spec]
+    return net, subs
+
+
+@pytest.mark.parametrize('seed,lstm_dim,K,spec', [
+    (1, 16, 3, [([0, 1, 2], 5)]),
+    (2, 32, 10, [([0, 1, 2, 3, 4, 5], 7), ([2], 1), ([0, 3], 64), ([1, 5, 4, 0], 3)]),
+    (3, 64, 4, [([2, 4], 130), ([5, 1, 5, 1, 5, 1, 0], 33), ([3], 257)]),
+])
+def test_loss_and_grads_vs_oracle_random(cuda, seed, lstm_dim, K, spec):
+    net, subs = _random_case(seed, lstm_dim, K, spec)
+    params = {k: v.cpu() for k, v in net.reference_state_dict().items()}
+    tsubs = [{k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in sb.items()} for sb in subs]
+    want_loss, want_grads, _ = onet.loss_and_grads(params, tsubs, ['o0', 'o1'], [3, 1], K)
+    success, loss = net._loss(synthetic.ArrayBatch(subs))
+    assert success
+    assert abs(float(loss) - float(want_loss)) <= 1e-4 * abs(float(want_loss))
+    loss.backward()
+    _check_grads(net, want_grads)
+
+
+def test_adam_step_vs_torch(cuda):
+    fx = netfixture.load('gum')
+    net = _net_from_fixture(fx)
+    batch = synthetic.ArrayBatch(_subs_numpy(fx['subs']))
+    from pyprob_b200.util import Optimizer
+    net._optimizer_type, net._learning_rate_init, net._weight_decay = Optimizer.ADAM, 1e-3, 1e-2
+    net._create_optimizer()
+    ref_p = net._arena.data.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref_p], lr=1e-3, weight_decay=1e-2)
+    for _ in range(3):
+        net._arena.grad = None
+        ok, loss = net._loss(batch)
+        loss.backward()
+        ref_p.grad = net._arena.grad.clone()
+        opt.step()
+        net.optimizer_step()
+    torch.testing.assert_close(net._arena.data, ref_p.data, rtol=1e-5, atol=1e-7)
+
+
+def test_loss_is_additive_over_sub_batches_and_grad_scales(cuda):
+    """Size-independent properties at a larger size: loss(batch) * B == sum_s loss(sub s) * B_s, and the
+    gradient is linear in the upstream gradient."""
+    net, subs = _random_case(7, 128, 10, [([0, 1, 2, 3], 300), ([2, 4, 5], 211), ([1], 77)])
+    full = synthetic.ArrayBatch(subs)
+    _, loss = net._loss(full)
+    parts = 0.0
+    for sb in subs:
+        b = synthetic.ArrayBatch([sb])
+        _, l = net._loss(b)
+        parts += float(l) * b.size
+    assert abs(float(loss) * full.size - parts) <= 2e-5 * abs(parts)
+    net._arena.grad = None
+    loss.backward()
+    g1 = net._arena.grad.clone()
+    net._arena.grad = None
+    _, loss2 = net._loss(full)
+    (loss2 * 3.0).backward()
+    torch.testing.assert_close(net._arena.grad, g1 * 3.0, rtol=2e-5, atol=1e-7)
