@@ -427,10 +427,15 @@ class InferenceNetworkLSTM(nn.Module):
         call('ppb_ic_loss_forward', self._handle, ptr(self._arena.data), C.byref(bs), ptr(self._workspace), need,
              self._precision, ptr(loss), ptr(status), ptr(row_lp), 1 if want_grad else 0, stream())
         enc._batch_struct = bs  # keep the decoded view for backward
+        self._generation = getattr(self, '_generation', 0) + 1
+        enc._generation = self._generation
         self._last_status = status
         return loss
 
     def _backward_native(self, enc, grad, grad_scale):
+        if getattr(enc, '_generation', None) != getattr(self, '_generation', 0):
+            raise RuntimeError('pyprob_b200: backward() must directly follow the _loss() that produced the loss — '
+                               'the activation workspace and the staged batch are shared between calls')
         need = self._ensure_workspace(enc)
         call('ppb_ic_loss_backward', self._handle, ptr(self._arena.data), ptr(grad), C.byref(enc._batch_struct),
              ptr(self._workspace), need, self._precision, grad_scale, stream())
@@ -568,7 +573,7 @@ class InferenceNetworkLSTM(nn.Module):
                 loss_value = float(packed[-1]) / world
                 grad_scale = 1.0 / world
             else:
-                loss_value = float(loss)
+                loss_value = float(loss.detach())
                 grad_scale = 1.0
             self._learning_rate = self._current_learning_rate()
             self.optimizer_step(grad_scale)
