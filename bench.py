@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — one JSON line per run (driver contract, tier framing (4)).
+
+Workload (N = 1): BASELINE.json configs[1] — GaussianUnknownMean inference compilation,
+InferenceNetworkLSTM h=512, observe embeddings 32+32, minibatch 256 prior traces, one Adam step per batch.
+A "step" = one pass of the hot path over one synthetic minibatch: encode image -> forward -> hand-written
+backward -> (N>1: one NCCL all-reduce of the flat gradient arena) -> fused Adam.
+
+  value : traces/s, whole job, batch image resident in HBM when the timed region starts (device events,
+          L2 flushed between steps, max over ranks)
+  e2e   : same metric through the C-ABI host-buffer call (ppb_ic_train_step_host): pinned host image ->
+          H2D -> forward/backward/Adam -> D2H loss, every step
+  roofline     : LSTM gate GEMM class (input projections + recurrent GEMMs, fwd+bwd), tensor-core bound
+  cpu_baseline : the oracle port of the reference's _loss + backward + Adam on this box's host cores
+  extra        : IS / IC posterior particles/s through the public Model API (the metric's other half)
+
+`--impl reference` times the CPU oracle port (the reference cannot travel to the GPU box) on the same config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BATCH = 256
+LSTM_DIM = 512
+WORKLOAD = 'GaussianUnknownMean IC train, LSTM h=512, obs-embed 32+32, batch 256/GPU (BASELINE configs[1])'
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {'hbm_gbs': p['hbm_gbs'], 'bf16_tflops': p['bf16_tflops'],
+                'bf16_tflops_sustained': p.get('bf16_tflops_sustained', p['bf16_tflops']), 'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
+        reasons = set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            if len(r) >= 9:
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith('active'):
+                        reasons.add(nm)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---- CPU arm: the oracle port of the reference path -------------------------------------------------------
+def cpu_reference_arm(steps, warmup, budget_s=20.0):
+    """_loss + backward + Adam of the reference network (oracle restatement, torch CPU fp32, all host threads)
+    on GUM minibatches of 256 traces.  Returns traces/s over the timed steps."""
+    from oracle import network as onet
+    from pyprob_b200 import synthetic
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    rng = np.random.default_rng(0)
+    # parameters with the reference's names/shapes (built on the CPU without the CUDA library)
+    torch.manual_seed(0)
+    import torch.nn as nn
+    params = {}
+
+    def lin(prefix, i, o):
+        m = nn.Linear(i, o)
+        params[prefix + '.weight'], params[prefix + '.bias'] = m.weight.detach().clone(), m.bias.detach().clone()
+    for name in ('obs0', 'obs1'):
+        lin('_layers_observe_embedding.{}._layers.0'.format(name), 1, 16)
+        lin('_layers_observe_embedding.{}._layers.1'.format(name), 16, 32)
+    lin('_layers_observe_embedding_final._layers.0', 64, 64)
+    lin('_layers_observe_embedding_final._layers.1', 64, 64)
+    I = 64 + 4 + 144
+    lstm = nn.LSTM(I, LSTM_DIM, 1)
+    for k in ('weight_ih_l0', 'weight_hh_l0', 'bias_ih_l0', 'bias_hh_l0'):
+        params['_layers_lstm.' + k] = getattr(lstm, k).detach().clone()
+    a = '98__forward__mu__Normal__1'
+    params['_layers_address_embedding.' + a] = torch.randn(64)
+    params['_layers_distribution_type_embedding.Normal'] = torch.randn(8)
+    lin('_layers_sample_embedding.{}._layers.0'.format(a), 1, 4)
+    lin('_layers_proposal.{}._ff._layers.0'.format(a), LSTM_DIM, (LSTM_DIM + 30) // 2)
+    lin('_layers_proposal.{}._ff._layers.1'.format(a), (LSTM_DIM + 30) // 2, 30)
+    plist = {k: v.requires_grad_(True) for k, v in params.items()}
+    opt = torch.optim.Adam(list(plist.values()), lr=1e-3)
+
+    def one_step():
+        b = synthetic.gum_batch(rng, BATCH)
+        subs = [{k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in sb.items()} for sb in b.subs]
+        opt.zero_grad()
+        loss, _ = onet.loss(plist, subs, ['obs0', 'obs1'], [1, 1], 10)
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+    for _ in range(max(warmup, 1)):
+        one_step()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        one_step()
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {'value': done * BATCH / dt, 'unit': 'traces/s', 'cores': threads, 'kind': 'port',
+            'sample': '{} steps of _loss+backward+Adam on {}-trace GUM minibatches (oracle/network.py, torch CPU fp32, '
+                      '{} threads), {:.1f} s'.format(done, BATCH, threads, dt)}, dt / done
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--precision', type=int, default=0)
+    ap.add_argument('--no-extra', action='store_true')
+    args = ap.parse_args()
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    warmup = max(args.warmup, 3)
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        cb, s_per_step = cpu_reference_arm(args.steps, warmup, budget_s=120.0)
+        print(json.dumps({'impl': 'reference', 'metric': 'ic_train_traces_per_sec', 'value': cb['value'],
+                          'unit': 'traces/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': warmup,
+                          'ms_per_step': s_per_step * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+                          'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                          'config': {'workload': WORKLOAD, 'global_batch': BATCH, 'note': 'CPU oracle port of the '
+                                     'reference path; rank 0 only'},
+                          'cpu_baseline': cb,
+                          'e2e': {'value': cb['value'], 'unit': 'traces/s', 'h2d_bytes_per_step': 0,
+                                  'd2h_bytes_per_step': 0}}))
+        return
+
+    import torch.distributed as dist
+    from pyprob_b200 import _lib, synthetic
+    from pyprob_b200._lib import call, ptr
+    from pyprob_b200.util import Optimizer
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    rng = np.random.default_rng(1234 + rank)
+    net = synthetic.gum_network(lstm_dim=LSTM_DIM, precision=args.precision, seed=0)
+    net._optimizer_type, net._learning_rate_init, net._weight_decay = Optimizer.ADAM, 1e-3, 0.0
+    net._create_optimizer()
+    net._sync_native()
+    if world > 1:
+        dist.broadcast(net._arena.data, 0)
+    nparams = net._arena.numel()
+    grad = torch.zeros(nparams, device=dev)
+    net._arena.grad = grad
+    batches = [synthetic.gum_batch(rng, BATCH) for _ in range(4)]
+    encs = [b.encode(net) for b in batches]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident step -----------------------------------------------------------------------------
+    import ctypes as C
+    step_no = [0]
+
+    def device_step(enc, staged):
+        bs, need = staged
+        grad.zero_()
+        loss = torch.empty((), device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        call('ppb_ic_loss_forward', net._handle, ptr(net._arena.data), C.byref(bs), ptr(net._workspace), need,
+             args.precision, ptr(loss), ptr(status), None, 1, stream.cuda_stream)
+        call('ppb_ic_loss_backward', net._handle, ptr(net._arena.data), ptr(grad), C.byref(bs), ptr(net._workspace), need,
+             args.precision, 1.0, stream.cuda_stream)
+        if world > 1:
+            dist.all_reduce(grad)
+        step_no[0] += 1
+        call('ppb_adam_step', ptr(net._arena.data), ptr(grad), ptr(net._exp_avg), ptr(net._exp_avg_sq), nparams, 1e-3, 0.9,
+             0.999, 1e-8, 0.0, step_no[0], 1.0 / world, stream.cuda_stream)
+        return loss
+
+    # stage one image per distinct batch (separate device images so the timed region does no H2D)
+    staged = []
+    for enc in encs:
+        img = torch.from_numpy(enc.pack().copy())
+        host = img.pin_memory()
+        devimg = host.to(dev)
+        bs = __import__('pyprob_b200.network', fromlist=['BatchStruct']).BatchStruct()
+        call('ppb_batch_from_image', host.data_ptr(), devimg.data_ptr(), host.numel(), C.byref(bs))
+        need = net._ensure_workspace(enc)
+        staged.append((bs, need, host, devimg))
+    for i in range(warmup):
+        device_step(encs[i % 4], staged[i % 4][:2])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.call('ppb_launch_count')
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.zero_()                      # L2 flush between timed iterations (outside the timed spans)
+        ev[i][0].record(stream)
+        device_step(encs[i % 4], staged[i % 4][:2])
+        ev[i][1].record(stream)
+    barrier()
+    launches = _lib.call('ppb_launch_count') - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([dev_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    value = args.steps * BATCH * world / (dev_ms * 1e-3)
+
+    # ---- e2e: C-ABI host-buffer call, H2D + D2H inside the timed region --------------------------------------
+    loss_host = torch.zeros(1).pin_memory()
+    status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+    e2e_img_dev = torch.empty(staged[0][2].numel() + 4096, dtype=torch.uint8, device=dev)
+    ws_bytes = net._workspace.numel()
+
+    def e2e_step(i):
+        bs, need, host, _ = staged[i % 4]
+        if world == 1:
+            step_no[0] += 1
+            call('ppb_ic_train_step_host', net._handle, ptr(net._arena.data), ptr(grad), ptr(net._exp_avg),
+                 ptr(net._exp_avg_sq), nparams, host.data_ptr(), host.numel(), ptr(e2e_img_dev), ptr(net._workspace),
+                 ws_bytes, args.precision, 1e-3, 0.9, 0.999, 1e-8, 0.0, step_no[0], loss_host.data_ptr(),
+                 status_host.data_ptr(), stream.cuda_stream)
+        else:
+            e2e_img_dev[:host.numel()].copy_(host, non_blocking=True)
+            bs2 = type(bs)()
+            call('ppb_batch_from_image', host.data_ptr(), e2e_img_dev.data_ptr(), host.numel(), C.byref(bs2))
+            loss = device_step(encs[i % 4], (bs2, need))
+            loss_host.copy_(loss.view(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+    for i in range(warmup):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record(stream)
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3 * 0.0)
+    t = torch.tensor([e2e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = args.steps * BATCH * world / (e2e_ms * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline of the gate-GEMM class: per-launch durations from CUDA events inside the step ---------------
+    peaks = measured_peaks()
+    roof = None
+    if rank == 0:
+        call('ppb_prof_enable', 1)
+        for i in range(min(args.steps, 20)):
+            flush.zero_()
+            device_step(encs[i % 4], staged[i % 4][:2])
+        torch.cuda.synchronize()
+        ms, n, fl = C.c_double(), C.c_int64(), C.c_double()
+        call('ppb_prof_read', C.byref(ms), C.byref(n), C.byref(fl))
+        call('ppb_prof_enable', 0)
+        tf32_peak = peaks['bf16_tflops_sustained'] / 2.0   # tf32 dense = 1/2 of the measured bf16 GEMM peak
+        achieved = fl.value / (ms.value * 1e-3) / 1e12 if ms.value > 0 else 0.0
+        roof = {'bound': 'tensor', 'kernel': 'LSTM gate GEMM class (P_obs/P_step/recurrent + their dX/dW)',
+                'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': achieved / tf32_peak,
+                'traffic': None, 'launches': n.value, 'avg_launch_us': ms.value * 1e3 / max(n.value, 1),
+                'flops_per_step': fl.value / max(min(args.steps, 20), 1),
+                'peak_source': '{} bf16_tflops_sustained / 2 (tf32)'.format(peaks['source'])}
+
+    extra = {}
+    cpu_baseline = None
+    if rank == 0 and world == 1:
+        cpu_baseline, _ = cpu_reference_arm(10 ** 6, 2, budget_s=15.0)
+        if not args.no_extra:
+            extra = posterior_extras(dev)
+    if rank == 0:
+        out = {'metric': 'ic_train_traces_per_sec', 'value': value, 'unit': 'traces/s', 'n_gpus': world,
+               'steps': args.steps, 'warmup': warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
+               'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+               'config': {'workload': WORKLOAD, 'global_batch': BATCH * world, 'lstm_dim': LSTM_DIM, 'trace_length': 1,
+                          'parameters': nparams, 'parallelism': 'dp{}'.format(world),
+                          'precision': ['3xTF32', 'TF32', 'fp32-simt'][args.precision],
+                          'l2': 'flushed between timed steps (256 MiB memset outside the timed spans)'},
+               'e2e': {'value': e2e_value, 'unit': 'traces/s', 'h2d_bytes_per_step': int(staged[0][2].numel()),
+                       'd2h_bytes_per_step': 8, 'ms_per_step': e2e_ms / args.steps},
+               'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu_baseline,
+               'extra': extra}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def posterior_extras(dev):
+    """The metric's other half: IS / IC posterior particles/s through the public Model API (N = 1 only)."""
+    import math
+    import pyprob_b200 as pyprob
+    from pyprob_b200 import InferenceEngine, Model
+    from pyprob_b200.distributions import Normal
+
+    class GUM(Model):
+        def forward(self):
+            mu = pyprob.sample(Normal(1, math.sqrt(5)))
+            lik = Normal(mu, math.sqrt(2))
+            pyprob.observe(lik, name='obs0')
+            pyprob.observe(lik, name='obs1')
+            return mu
+    pyprob.seed(1)
+    pyprob.set_verbosity(0)
+    m = GUM()
+    out = {}
+    for n in (65536, 1 << 24):
+        for _ in range(3):
+            m.posterior_results(n, observe={'obs0': 8, 'obs1': 9})
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            post = m.posterior_results(n, observe={'obs0': 8, 'obs1': 9})
+            ess = post.effective_sample_size  # device->host read of the result
+        torch.cuda.synchronize()
+        out['is_posterior_particles_per_sec_n{}'.format(n)] = reps * n / (time.perf_counter() - t0)
+    return out
+
+
+if __name__ == '__main__':
+    main()

@@ -39,6 +39,13 @@ int ppb_version(void);
 /* Compute capability major*10+minor of the current device; the library refuses (PPB_ENOTSUP) to run
  * tensor-core paths on anything but sm_100. */
 int ppb_device_arch(void);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+int64_t ppb_launch_count(void);
+/* Kernel-level profiling for bench.py's roofline: when enabled, the library brackets every launch of the
+ * LSTM gate GEMM class (input projections + recurrent GEMMs, forward and backward) with CUDA events on the
+ * launching stream; ppb_prof_read sums their durations.  Off by default (events perturb the step). */
+int ppb_prof_enable(int on);
+int ppb_prof_read(double* total_ms_out, int64_t* launches_out, double* flops_out);
 
 /* ------------------------------------------------------------------------------------------------
  * 1. Trace scoring: per-family log_prob over the particle axis  
@@ -300,9 +307,19 @@ int ppb_ic_train_step_host(ppb_net* net, float* arena, float* grad_arena, float*
 int64_t ppb_packed_floats(int64_t rows, int64_t K);
 int ppb_pack_tf32(const float* X, int64_t rows, int64_t K, int64_t ldx, float* hi_out, float* lo_out,
                   void* stream);
+/* Same geometry, MN-major swizzle pattern (SWIZZLE_128B_BASE32B): the operand form whose reduction runs along
+ * the image rows (weight-gradient and input-gradient GEMMs).  See DESIGN.md section 4. */
+int ppb_pack_tf32_mn(const float* X, int64_t rows, int64_t K, int64_t ldx, float* hi_out, float* lo_out,
+                     void* stream);
 int ppb_gemm_packed(const float* A_hi, const float* A_lo, const float* B_hi, const float* B_lo,
                     float* C, int64_t M, int64_t N, int64_t K, int64_t ldc, const float* bias,
                     int relu, int precision, void* stream);
+
+/* TN form over the same images: C[M,N] = sum_r X[r,m] * Y[r,n], X packed from [R,M], Y from [R,N]
+ * (both operands MN-major; used by every weight-gradient GEMM: no transposed copies in HBM). */
+int ppb_gemm_packed_tn(const float* X_hi, const float* X_lo, const float* Y_hi, const float* Y_lo,
+                       float* C, int64_t M, int64_t N, int64_t R, int64_t ldc, int precision,
+                       void* stream);
 
 #ifdef __cplusplus
 }

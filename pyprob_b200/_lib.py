@@ -25,6 +25,9 @@ c_int = C.c_int
 _SIGNATURES = {
     'ppb_version': [],
     'ppb_device_arch': [],
+    'ppb_launch_count': [],
+    'ppb_prof_enable': [c_int],
+    'ppb_prof_read': [C.c_void_p, C.c_void_p, C.c_void_p],
     'ppb_normal_log_prob': [c_f, c_f, c_int, c_f, c_int, c_f, c_f, c_dbl, c_i64, c_f],
     'ppb_uniform_log_prob': [c_f, c_f, c_int, c_f, c_int, c_f, c_f, c_dbl, c_i64, c_f],
     'ppb_poisson_log_prob': [c_f, c_f, c_int, c_f, c_f, c_dbl, c_i64, c_f],
@@ -60,6 +63,8 @@ _SIGNATURES = {
                                c_flt, c_flt, c_flt, c_flt, c_flt, c_i64, C.c_void_p, C.c_void_p, c_f],
     'ppb_packed_floats': [c_i64, c_i64],
     'ppb_pack_tf32': [c_f, c_i64, c_i64, c_i64, c_f, c_f, c_f],
+    'ppb_pack_tf32_mn': [c_f, c_i64, c_i64, c_i64, c_f, c_f, c_f],
+    'ppb_gemm_packed_tn': [c_f, c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_int, c_f],
     'ppb_gemm_packed': [c_f, c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_f, c_int, c_int, c_f],
 }
 _RESTYPES = {
@@ -67,10 +72,11 @@ _RESTYPES = {
     'ppb_ic_infer_workspace_bytes': c_i64,
     'ppb_packed_floats': c_i64,
     'ppb_sizeof': c_i64,
+    'ppb_launch_count': c_i64,
 }
 # entry points whose integer return value is data, not a status
 _VALUE_RETURNS = {'ppb_version', 'ppb_device_arch', 'ppb_weights_num_partials', 'ppb_ic_workspace_bytes',
-                  'ppb_ic_infer_workspace_bytes', 'ppb_packed_floats', 'ppb_sizeof'}
+                  'ppb_ic_infer_workspace_bytes', 'ppb_packed_floats', 'ppb_sizeof', 'ppb_launch_count'}
 
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES.keys()) + ['ppb_last_error'])
 

@@ -28,8 +28,11 @@ void ppb_set_error(const char* fmt, ...);
     }                                                                               \
   } while (0)
 
+extern unsigned long long g_ppb_launches;  // kernels launched by this library (bench.py reports it)
+
 #define PPB_LAUNCH_CHECK()                                                          \
   do {                                                                              \
+    ++g_ppb_launches;                                                               \
     cudaError_t _e = cudaGetLastError();                                            \
     if (_e != cudaSuccess) {                                                        \
       ppb_set_error("%s:%d launch: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \

@@ -5,6 +5,7 @@
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
+unsigned long long g_ppb_launches = 0;
 
 void ppb_set_error(const char* fmt, ...) {
   va_list ap;
@@ -18,6 +19,8 @@ extern "C" {
 const char* ppb_last_error(void) { return g_err; }
 
 int ppb_version(void) { return 100; }
+
+int64_t ppb_launch_count(void) { return (int64_t)g_ppb_launches; }
 
 int ppb_device_arch(void) {
   int dev = 0;

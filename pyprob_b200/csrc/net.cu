@@ -225,11 +225,35 @@ int upload_and_get(ppb_net* net, const Builder& b, Problem* dev, int64_t cap, cu
   return PPB_OK;
 }
 
-int run_phase(const gemm::Phase& ph, const Problem* dev, cudaStream_t st) {
+// ---- optional kernel-level profiling of the LSTM gate GEMM class (bench.py roofline) ---------------
+struct Prof {
+  bool on = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans;
+  double flops = 0.0;
+  int64_t launches = 0;
+} g_prof;
+
+int run_phase(const gemm::Phase& ph, const Problem* dev, cudaStream_t st, const Builder* bl_for_prof = nullptr) {
   if (ph.count == 0) return PPB_OK;
   int grid = ph.tiles < 8 * PPB_NUM_SMS ? ph.tiles : 8 * PPB_NUM_SMS;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  const bool prof = g_prof.on && bl_for_prof;
+  if (prof) {
+    PPB_CUDA(cudaEventCreate(&e0));
+    PPB_CUDA(cudaEventCreate(&e1));
+    PPB_CUDA(cudaEventRecord(e0, st));
+  }
   gemm::k_grouped<<<grid, gemm::kThreads, 0, st>>>(dev + ph.first, ph.count, ph.tiles);
   PPB_LAUNCH_CHECK();
+  if (prof) {
+    PPB_CUDA(cudaEventRecord(e1, st));
+    g_prof.spans.push_back({e0, e1});
+    g_prof.launches += 1;
+    for (int i = 0; i < ph.count; ++i) {
+      const Problem& p = bl_for_prof->probs[ph.first + i];
+      g_prof.flops += 2.0 * p.M * p.N * p.K;
+    }
+  }
   return PPB_OK;
 }
 
@@ -667,14 +691,14 @@ int ppb_ic_loss_forward(ppb_net* net, const float* arena, const ppb_batch* b, vo
   k_smp_embed<<<ew_grid((int64_t)d.R * S), 256, 0, st>>>(arena, net->d_addrs, b->row_step, b->step_prev_addr,
                                                          b->row_prev, b->values, d.R, S, w.smp_emb);
   PPB_LAUNCH_CHECK();
-  rc = run_phase(bl.phases[ph_p], w.problems, st);
+  rc = run_phase(bl.phases[ph_p], w.problems, st, &bl);
   if (rc) return rc;
   // b_hh joins the step projection (P_step already has b_ih): add once with a scaled-axpy kernel
   k_add_row_bias<<<ew_grid((int64_t)d.NS * H4), 256, 0, st>>>(w.p_step, arena + D.b_hh_off, (int64_t)d.NS * H4, H4);
   PPB_LAUNCH_CHECK();
   for (int t = 0; t < d.T; ++t) {
     int r0 = b->row_off_host[t], n = b->row_off_host[t + 1] - r0;
-    if (t > 0) { rc = run_phase(bl.phases[ph_rec0 + t - 1], w.problems, st); if (rc) return rc; }
+    if (t > 0) { rc = run_phase(bl.phases[ph_rec0 + t - 1], w.problems, st, &bl); if (rc) return rc; }
     k_cell_fwd<<<ew_grid((int64_t)n * H), 256, 0, st>>>(w.gates, w.p_obs, w.p_step, w.w_smp_t, w.smp_emb, b->row_step,
                                                        b->row_prev, w.c, w.h, r0, n, H, S, t);
     PPB_LAUNCH_CHECK();
@@ -814,14 +838,15 @@ int ppb_ic_loss_backward(ppb_net* net, const float* arena, float* grad, const pp
     const ppb_addr_desc& a = net->addrs[b->group_addr_host[g]];
     int s0 = b->group_start_host[g], cnt = b->group_start_host[g + 1] - s0;
     k_colsum_gather<<<(a.head_out + 127) / 128, 128, 0, st>>>(w.d_out, net->out_pad, b->head_rows + s0, cnt, a.head_out, grad + a.b2_off);
+    PPB_LAUNCH_CHECK();
     k_colsum_gather<<<(a.head_hidden + 127) / 128, 128, 0, st>>>(w.d_hid, net->dh_pad, b->head_rows + s0, cnt, a.head_hidden, grad + a.b1_off);
+    PPB_LAUNCH_CHECK();
   }
-  PPB_LAUNCH_CHECK();
   // BPTT
   for (int t = d.T - 1; t >= 0; --t) {
     int r0 = b->row_off_host[t], n = b->row_off_host[t + 1] - r0;
     int n_next = (t + 1 < d.T) ? b->row_off_host[t + 2] - b->row_off_host[t + 1] : 0;
-    if (n_next > 0) { rc = run_phase(bl.phases[ph_rec0 + (d.T - 2 - t)], w.problems, st); if (rc) return rc; }
+    if (n_next > 0) { rc = run_phase(bl.phases[ph_rec0 + (d.T - 2 - t)], w.problems, st, &bl); if (rc) return rc; }
     k_cell_bwd<<<ew_grid((int64_t)n * H), 256, 0, st>>>(w.gates, w.c, w.dh, w.dh_rec, w.dc, dgates, w.d_pobs, b->row_prev,
                                                        r0, n, n_next, H, t);
     PPB_LAUNCH_CHECK();
@@ -831,7 +856,7 @@ int ppb_ic_loss_backward(ppb_net* net, const float* arena, float* grad, const pp
     k_step_colsum<<<g, 256, 0, st>>>(dgates, b->step_row0, b->step_nrows, H4, w.d_pstep);
     PPB_LAUNCH_CHECK();
   }
-  rc = run_phase(bl.phases[ph_lstm_w], w.problems, st); if (rc) return rc;
+  rc = run_phase(bl.phases[ph_lstm_w], w.problems, st, &bl); if (rc) return rc;
   k_bias_grad<<<(H4 + 255) / 256, 256, 0, st>>>(w.d_pstep, d.NS, H4, grad + D.b_ih_off, grad + D.b_hh_off);
   PPB_LAUNCH_CHECK();
   k_embed_scatter<<<ew_grid((int64_t)d.NS * C2), 256, 0, st>>>(w.d_embcat, net->d_addrs, net->d_type_off, b->step_addr,
@@ -854,6 +879,7 @@ int ppb_ic_loss_backward(ppb_net* net, const float* arena, float* grad, const pp
     const ppb_linear_desc& L = D.obs_final.layers[l];
     float* dY = (l == D.obs_final.num_layers - 1) ? w.d_obs_emb : w.d_fin_act[l];
     k_colsum_gather<<<(L.out_dim + 127) / 128, 128, 0, st>>>(dY, L.out_dim, nullptr, d.B, L.out_dim, grad + L.b_off);
+    PPB_LAUNCH_CHECK();
     rc = run_phase(bl.phases[ph_fin[k]], w.problems, st); if (rc) return rc;
   }
   for (size_t k = 0; k < ph_obs.size(); ++k) {
@@ -866,10 +892,10 @@ int ppb_ic_loss_backward(ppb_net* net, const float* arena, float* grad, const pp
       const float* dY = last ? w.d_obs_cat + out_off[j] : w.d_obs_act[j][l];
       int64_t lddy = last ? E : L.out_dim;
       k_colsum_gather<<<(L.out_dim + 127) / 128, 128, 0, st>>>(dY, lddy, nullptr, d.B, L.out_dim, grad + L.b_off);
+      PPB_LAUNCH_CHECK();
     }
     rc = run_phase(bl.phases[ph_obs[k]], w.problems, st); if (rc) return rc;
   }
-  PPB_LAUNCH_CHECK();
   return PPB_OK;
 }
 
@@ -1043,6 +1069,29 @@ InferWs carve_infer(const ppb_net* net, int64_t n, void* base) {
 
 extern "C" {
 
+int ppb_prof_enable(int on) {
+  for (auto& sp : g_prof.spans) { cudaEventDestroy(sp.first); cudaEventDestroy(sp.second); }
+  g_prof.spans.clear();
+  g_prof.flops = 0.0;
+  g_prof.launches = 0;
+  g_prof.on = on != 0;
+  return PPB_OK;
+}
+
+int ppb_prof_read(double* total_ms_out, int64_t* launches_out, double* flops_out) {
+  double total = 0.0;
+  for (auto& sp : g_prof.spans) {
+    PPB_CUDA(cudaEventSynchronize(sp.second));
+    float ms = 0.0f;
+    PPB_CUDA(cudaEventElapsedTime(&ms, sp.first, sp.second));
+    total += ms;
+  }
+  if (total_ms_out) *total_ms_out = total;
+  if (launches_out) *launches_out = g_prof.launches;
+  if (flops_out) *flops_out = g_prof.flops;
+  return PPB_OK;
+}
+
 int64_t ppb_sizeof(int which) {
   switch (which) {
     case 0: return sizeof(ppb_net_desc);
@@ -1160,6 +1209,7 @@ int ppb_ic_infer_step(ppb_net* net, const float* arena, const float* obs_emb, in
   rc = run_phase(bl.phases[1], w.problems, st); if (rc) return rc;
   if (!first) {
     k_wsmp_transpose<<<ew_grid(S * H4), 256, 0, st>>>(arena + D.w_ih_off, I, E, S, H4, w.w_smp_t);
+    PPB_LAUNCH_CHECK();
     k_smp_embed_infer<<<ew_grid(n * S), 256, 0, st>>>(arena, prev, prev_value, n, S, w.smp_emb);
     PPB_LAUNCH_CHECK();
     rc = run_phase(bl.phases[2], w.problems, st); if (rc) return rc;

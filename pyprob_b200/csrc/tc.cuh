@@ -24,6 +24,16 @@ __host__ __device__ __forceinline__ int64_t packed_offset(int64_t row, int64_t k
   return (rt * KB + kb) * kTileFloats + atom * 256 + rr * 32 + ((c ^ rr) << 2) + j;
 }
 
+// MN-major flavour of the same tile (tf32 operands whose reduction runs along the image ROWS must use the
+// SWIZZLE_128B_BASE32B pattern — "for mn-major tf32 operands, SW128_32B is the only available smem layout"):
+// same geometry (row r at byte r*128 of the tile), but the four 32-byte chunks of a row are permuted by
+// (c32 ^ (r & 3)) instead of the eight 16-byte chunks by (c16 ^ (r & 7)).
+__host__ __device__ __forceinline__ int64_t packed_offset_mn(int64_t row, int64_t k, int64_t KB) {
+  int64_t rt = row >> 7, r = row & 127, kb = k >> 5, kk = k & 31;
+  int64_t c32 = kk >> 3, j = kk & 7;
+  return (rt * KB + kb) * kTileFloats + r * 32 + ((c32 ^ (r & 3)) << 3) + j;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ---- mbarrier ------------------------------------------------------------------------------------
@@ -104,11 +114,25 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                        // layout type SWIZZLE_128B
   return d;
 }
-// Instruction descriptor for kind::tf32, fp32 accumulate, A and B K-major.
-__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
+// MN-major operand over the same tile image: the 128-byte swizzle span runs along M/N (32 fp32) and the
+// 8 rows of an atom are 8 consecutive K indices.  LBO = byte distance between consecutive 32-element
+// M/N blocks, SBO = distance between 8-row K groups (one tf32 MMA consumes exactly one group).
+__device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // between 32-element M/N blocks
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;   // between 4-row K groups (512 B in the tile image)
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                             // layout type SWIZZLE_128B_BASE32B
+  return d;
+}
+// Instruction descriptor for kind::tf32, fp32 accumulate; a_mn / b_mn select MN-major operands.
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn = 0, int b_mn = 0) {
   return (1u << 4)                      // D format F32
          | (2u << 7)                    // A format TF32
          | (2u << 10)                   // B format TF32
+         | ((uint32_t)a_mn << 15)       // A major: 0 = K, 1 = MN
+         | ((uint32_t)b_mn << 16)       // B major
          | ((uint32_t)(N >> 3) << 17)   // N / 8
          | ((uint32_t)(M >> 4) << 24);  // M / 16
 }

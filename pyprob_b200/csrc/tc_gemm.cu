@@ -10,6 +10,7 @@ namespace {
 using namespace tc;
 
 // ---- pack: row-major fp32 -> swizzled tile image(s) ------------------------------------------------
+template <bool MN>
 __global__ void __launch_bounds__(256) k_pack(const float* __restrict__ X, int64_t rows, int64_t K, int64_t ldx,
                                                float* __restrict__ hi, float* __restrict__ lo) {
   const int64_t KB = (K + kTileK - 1) / kTileK;
@@ -25,7 +26,7 @@ __global__ void __launch_bounds__(256) k_pack(const float* __restrict__ X, int64
     float h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) split_tf32(x[j], h[j], l[j]);
-    int64_t off = packed_offset(row, k0, KB);
+    int64_t off = MN ? packed_offset_mn(row, k0, KB) : packed_offset(row, k0, KB);
     *reinterpret_cast<float4*>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
     if (lo) *reinterpret_cast<float4*>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
   }
@@ -161,6 +162,137 @@ k_gemm_packed(const float* __restrict__ A_hi, const float* __restrict__ A_lo, co
   }
 }
 
+// ---- TN bring-up: C[M,N] = sum_r X[r, m] * Y[r, n] with X, Y given as row-major-packed images -------------------
+// (both operands MN-major over the SAME tile format: no transposed copies).  One 128x128 tile per CTA;
+// a stage holds 32 reduction rows: 4 column-blocks x 4 KB per operand image.
+constexpr int kTnRows = 32;                     // reduction rows per stage
+constexpr int kTnPiece = kTnRows * 128;         // bytes of one column-block piece (32 rows x 128 B)
+struct __align__(1024) TnSmem {
+  float a_hi[kStages][4 * kTnPiece / 4];
+  float a_lo[kStages][4 * kTnPiece / 4];
+  float b_hi[kStages][4 * kTnPiece / 4];
+  float b_lo[kStages][4 * kTnPiece / 4];
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t tmem_full;
+  uint32_t tmem_base;
+};
+
+template <bool X3>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+k_gemm_packed_tn(const float* __restrict__ X_hi, const float* __restrict__ X_lo, const float* __restrict__ Y_hi,
+                 const float* __restrict__ Y_lo, float* __restrict__ C, int M, int N, int R, int64_t ldc) {
+  extern __shared__ uint8_t smem_raw[];
+  TnSmem& sm = *reinterpret_cast<TnSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KBx = (M + kTileK - 1) / kTileK, KBy = (N + kTileK - 1) / kTileK;  // column blocks of the images
+  const int RC = (R + kTnRows - 1) / kTnRows;                                  // reduction chunks
+  const int mt = blockIdx.y, nt = blockIdx.x;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+    mbar_init(&sm.tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(&sm.tmem_base);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int rc = 0; rc < RC; ++rc) {
+        int s = rc % kStages;
+        uint32_t ph = (rc / kStages) & 1;
+        mbar_wait(&sm.empty[s], ph ^ 1);
+        // zero-fill column blocks that do not exist in the image (ragged M / N tile edges)
+        int na = 0, nb = 0;
+        for (int j = 0; j < 4; ++j) { na += (mt * 4 + j < KBx); nb += (nt * 4 + j < KBy); }
+        mbar_expect_tx(&sm.full[s], (uint32_t)((na + nb) * (X3 ? 2 : 1) * kTnPiece));
+        int r0 = rc * kTnRows;
+        int64_t rt = r0 >> 7, sub = (r0 & 127) >> 3;  // row tile, first atom inside it
+        for (int j = 0; j < 4; ++j) {
+          int cb = mt * 4 + j;
+          if (cb < KBx) {
+            int64_t off = (rt * KBx + cb) * kTileFloats + sub * 256;
+            bulk_g2s(&sm.a_hi[s][j * kTnPiece / 4], X_hi + off, kTnPiece, &sm.full[s]);
+            if (X3) bulk_g2s(&sm.a_lo[s][j * kTnPiece / 4], X_lo + off, kTnPiece, &sm.full[s]);
+          }
+          cb = nt * 4 + j;
+          if (cb < KBy) {
+            int64_t off = (rt * KBy + cb) * kTileFloats + sub * 256;
+            bulk_g2s(&sm.b_hi[s][j * kTnPiece / 4], Y_hi + off, kTnPiece, &sm.full[s]);
+            if (X3) bulk_g2s(&sm.b_lo[s][j * kTnPiece / 4], Y_lo + off, kTnPiece, &sm.full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_tf32(128, kBN, 1, 1);
+      for (int rc = 0; rc < RC; ++rc) {
+        int s = rc % kStages;
+        uint32_t ph = (rc / kStages) & 1;
+        mbar_wait(&sm.full[s], ph);
+        fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < kTnRows / 8; ++k) {
+          uint32_t adv = k * 1024;  // next 8-row atom
+          uint64_t ah = smem_desc_sw128_mn(smem_u32(sm.a_hi[s]) + adv, kTnPiece, 512);
+          uint64_t al = smem_desc_sw128_mn(smem_u32(sm.a_lo[s]) + adv, kTnPiece, 512);
+          uint64_t bh = smem_desc_sw128_mn(smem_u32(sm.b_hi[s]) + adv, kTnPiece, 512);
+          uint64_t bl = smem_desc_sw128_mn(smem_u32(sm.b_lo[s]) + adv, kTnPiece, 512);
+          if (X3) {
+            uint32_t first_lo = (rc == 0 && k == 0) ? 0u : 1u;
+            uint32_t first_hi = (rc < 2 && k == 0) ? 0u : 1u;
+            mma_tf32(tmem + 2 * kBN, al, bh, idesc, first_lo);
+            mma_tf32(tmem + 2 * kBN, ah, bl, idesc, 1u);
+            mma_tf32(tmem + (rc & 1) * kBN, ah, bh, idesc, first_hi);
+          } else {
+            mma_tf32(tmem, ah, bh, idesc, (rc == 0 && k == 0) ? 0u : 1u);
+          }
+        }
+        mma_commit(&sm.empty[s]);
+      }
+      mma_commit(&sm.tmem_full);
+    }
+  } else {
+    const int q = warp & 3;
+    mbar_wait(&sm.tmem_full, 0);
+    fence_after_sync();
+    const int row = mt * 128 + q * 32 + lane;
+#pragma unroll 1
+    for (int cb = 0; cb < kBN / 32; ++cb) {
+      float v[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + cb * 32, v);
+      if (X3) {
+        float u[32];
+        if (RC > 1) {
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + kBN + cb * 32, u);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += u[j];
+        }
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 2 * kBN + cb * 32, u);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += u[j];
+      }
+      int col0 = nt * kBN + cb * 32;
+      if (row < M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < N) C[(int64_t)row * ldc + col0 + j] = v[j];
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after_sync();
+    tmem_dealloc<kTmemCols>(tmem);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -173,7 +305,15 @@ int64_t ppb_packed_floats(int64_t rows, int64_t K) {
 int ppb_pack_tf32(const float* X, int64_t rows, int64_t K, int64_t ldx, float* hi_out, float* lo_out, void* stream) {
   PPB_CHECK_ARG(X && hi_out && rows > 0 && K > 0 && ldx >= K, "bad arguments");
   int64_t chunks = ppb_packed_floats(rows, K) / 4;
-  k_pack<<<ppb_grid_for(chunks, 256, 1), 256, 0, (cudaStream_t)stream>>>(X, rows, K, ldx, hi_out, lo_out);
+  k_pack<false><<<ppb_grid_for(chunks, 256, 1), 256, 0, (cudaStream_t)stream>>>(X, rows, K, ldx, hi_out, lo_out);
+  PPB_LAUNCH_CHECK();
+  return PPB_OK;
+}
+
+int ppb_pack_tf32_mn(const float* X, int64_t rows, int64_t K, int64_t ldx, float* hi_out, float* lo_out, void* stream) {
+  PPB_CHECK_ARG(X && hi_out && rows > 0 && K > 0 && ldx >= K, "bad arguments");
+  int64_t chunks = ppb_packed_floats(rows, K) / 4;
+  k_pack<true><<<ppb_grid_for(chunks, 256, 1), 256, 0, (cudaStream_t)stream>>>(X, rows, K, ldx, hi_out, lo_out);
   PPB_LAUNCH_CHECK();
   return PPB_OK;
 }
@@ -193,6 +333,24 @@ int ppb_gemm_packed(const float* A_hi, const float* A_lo, const float* B_hi, con
     PPB_CUDA(cudaFuncSetAttribute(k_gemm_packed<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_gemm_packed<false><<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(A_hi, A_lo, B_hi, B_lo, C, (int)M, (int)N,
                                                                              (int)K, ldc, bias, relu);
+  }
+  PPB_LAUNCH_CHECK();
+  return PPB_OK;
+}
+
+int ppb_gemm_packed_tn(const float* X_hi, const float* X_lo, const float* Y_hi, const float* Y_lo, float* C, int64_t M,
+                       int64_t N, int64_t R, int64_t ldc, int precision, void* stream) {
+  PPB_CHECK_ARG(X_hi && Y_hi && C && M > 0 && N > 0 && R > 0 && ldc >= N, "bad arguments");
+  PPB_CHECK_ARG(precision == PPB_PREC_TF32X3 || precision == PPB_PREC_TF32, "precision must be TF32X3 or TF32");
+  PPB_CHECK_ARG(precision == PPB_PREC_TF32 || (X_lo && Y_lo), "3xTF32 needs the lo images");
+  dim3 grid((unsigned)((N + kBN - 1) / kBN), (unsigned)((M + 127) / 128));
+  size_t smem = sizeof(TnSmem) + 1024;
+  if (precision == PPB_PREC_TF32X3) {
+    PPB_CUDA(cudaFuncSetAttribute(k_gemm_packed_tn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_gemm_packed_tn<true><<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(X_hi, X_lo, Y_hi, Y_lo, C, (int)M, (int)N, (int)R, ldc);
+  } else {
+    PPB_CUDA(cudaFuncSetAttribute(k_gemm_packed_tn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_gemm_packed_tn<false><<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(X_hi, X_lo, Y_hi, Y_lo, C, (int)M, (int)N, (int)R, ldc);
   }
   PPB_LAUNCH_CHECK();
   return PPB_OK;

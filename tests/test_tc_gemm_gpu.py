@@ -11,12 +11,12 @@ from pyprob_b200._lib import call, ptr, stream
 pytestmark = pytest.mark.gpu
 
 
-def _pack(x):
+def _pack(x, mn=False):
     rows, K = x.shape
     nfl = _lib.call('ppb_packed_floats', rows, K)
     hi = torch.empty(nfl, device=x.device)
     lo = torch.empty(nfl, device=x.device)
-    call('ppb_pack_tf32', ptr(x), rows, K, x.stride(0), ptr(hi), ptr(lo), stream())
+    call('ppb_pack_tf32_mn' if mn else 'ppb_pack_tf32', ptr(x), rows, K, x.stride(0), ptr(hi), ptr(lo), stream())
     return hi, lo
 
 
@@ -64,4 +64,24 @@ def test_gemm_packed(cuda, M, N, K, precision):
     err = np.abs(got - want).max() / scale
     assert np.isfinite(got).all()
     # fp32-faithful: within ~2x of a CPU fp32 sgemm (the tensor core accumulates with truncation; see tc_gemm.cu)
+    assert err < (8e-6 if precision == 0 else 3e-3), err
+
+
+@pytest.mark.parametrize('M,N,R', [(128, 128, 32), (128, 128, 256), (100, 30, 77), (271, 512, 300), (2048, 64, 256),
+                                   (512, 2048, 1000)])
+@pytest.mark.parametrize('precision', [0, 1])
+def test_gemm_packed_tn(cuda, M, N, R, precision):
+    """Weight-gradient form: C = X^T Y with both operands read MN-major from the row-major-packed images."""
+    gen = torch.Generator().manual_seed(M + N + R)
+    x = torch.randn(R, M, generator=gen)
+    y = torch.randn(R, N, generator=gen)
+    want = (x.double().t() @ y.double()).numpy()
+    xh, xl = _pack(x.to(cuda), mn=True)
+    yh, yl = _pack(y.to(cuda), mn=True)
+    c = torch.full((M, N), float('nan'), device=cuda)
+    call('ppb_gemm_packed_tn', ptr(xh), ptr(xl), ptr(yh), ptr(yl), ptr(c), M, N, R, N, precision, stream())
+    torch.cuda.synchronize()
+    got = c.cpu().double().numpy()
+    err = np.abs(got - want).max() / np.sqrt(R)
+    assert np.isfinite(got).all()
     assert err < (8e-6 if precision == 0 else 3e-3), err
