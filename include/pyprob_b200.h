@@ -229,13 +229,26 @@ typedef struct {
   const float* prior0;           /* [R]   prior mean | low                                    */
   const float* prior1;           /* [R]   prior stddev | high                                 */
   const float* obs;              /* [B, obs_in_total] flattened observed values               */
-  const int32_t* head_rows;      /* [R] row ids grouped by address                            */
+  const int32_t* head_rows;      /* [valid rows] row ids grouped by address                   */
+  const int32_t* row_trace;      /* [R]   trace index of the row, -1 for padding rows             */
+  const int32_t* row_next;       /* [R]   row of the same trace at t+1, -1 if the trace ends      */
+  const int32_t* step_t;         /* [n_steps] time index of the step                              */
+  const int32_t* step_prev_row0; /* [n_steps] first row of the same sub-batch at t-1 (-1 at t=0)  */
+  /* host copies of the per-step arrays (planning of the tensor-core path) */
+  const int32_t* step_addr_host;
+  const int32_t* step_row0_host;
+  const int32_t* step_nrows_host;
+  const int32_t* step_t_host;
+  const int32_t* step_prev_row0_host;
+  int32_t row_align;             /* 1 = compact rows, 128 = every (t, sub-batch) segment padded to 128 rows */
+  int32_t reserved2_;
 } ppb_batch;
 
 /* Batch image header: int64[PPB_IMAGE_HEADER_WORDS]; word 0 = magic, 1..7 = the seven int32 fields
  * above in order, 8 = total bytes, 9.. = byte offsets of the arrays in the order they are declared
  * above (row_off, group_addr, group_start, trace_sub, step_addr, step_prev_addr, step_row0, step_nrows,
- * row_step, row_prev, values, prior0, prior1, obs, head_rows).  Every array is 16-byte aligned. */
+ * row_step, row_prev, values, prior0, prior1, obs, head_rows, row_trace, row_next, step_t, step_prev_row0);
+ * word 28 = row_align.  Every array is 16-byte aligned. */
 #define PPB_IMAGE_MAGIC 0x5050423230304231LL
 #define PPB_IMAGE_HEADER_WORDS 32
 int ppb_batch_from_image(const void* image_host, const void* image_dev, int64_t image_bytes,

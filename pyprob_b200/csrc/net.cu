@@ -10,14 +10,45 @@
 // which removes the T-fold recomputation of the observation block.
 #include <vector>
 #include <string.h>
+#include <stdint.h>
 
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "heads.cuh"
+#include "tc_grouped.cuh"
 
 using gemm::Problem;
 
+// tile images of one tensor (either format may be absent); passed by value to element-wise kernels
+struct HImg {
+  float* k_hi = nullptr; float* k_lo = nullptr; float* mn_hi = nullptr; float* mn_lo = nullptr;
+  int64_t kb = 0;
+};
+
+struct WImg {  // tile images of one weight matrix (float offsets into ppb_net::wimg)
+  int64_t k_hi = 0, k_lo = 0, mn_hi = 0, mn_lo = 0;
+  int kb = 0;
+};
+struct PackEntry {  // one matrix of the weight-packing table
+  int64_t src_off;  // floats from the arena base
+  int rows, cols, ld, kb;
+  int64_t k_hi, k_lo, mn_hi, mn_lo;
+  int tile_start, pad_;
+};
+
 struct ppb_net {
+  // tensor-core path: packed tf32 images of every GEMM weight, refreshed from the arena each forward
+  float* wimg = nullptr;
+  int64_t wimg_floats = 0;
+  std::vector<PackEntry> pack;
+  PackEntry* d_pack = nullptr;
+  int pack_tiles = 0;
+  WImg w_ihE, w_hh;
+  std::vector<WImg> w1, w2;
+  void* h_blob[2] = {nullptr, nullptr};
+  cudaEvent_t ev_blob[2] = {nullptr, nullptr};
+  size_t blob_cap = 0;
+  int blob_idx = 0;
   ppb_net_desc desc;
   std::vector<ppb_addr_desc> addrs;
   std::vector<int64_t> type_off;
@@ -92,8 +123,8 @@ Ws carve(const ppb_net* net, Dims d, void* base) {
   w.loss_acc = take(64);
   w.d_hid = take((int64_t)d.R * net->dh_pad);
   w.dh = take((int64_t)d.R * H);
-  w.dh_rec = take((int64_t)d.B * H);
-  w.dc = take((int64_t)d.B * H);
+  w.dh_rec = take((int64_t)d.R * H);
+  w.dc = take((int64_t)d.R * H);
   w.d_pobs = take((int64_t)d.B * 4 * H);
   w.d_pstep = take((int64_t)d.NS * 4 * H);
   w.d_smp = take((int64_t)d.R * S);
@@ -321,18 +352,27 @@ __global__ void k_smp_embed(const float* __restrict__ arena, const ppb_addr_desc
 __global__ void __launch_bounds__(256) k_cell_fwd(float* __restrict__ gates, const float* __restrict__ p_obs,
                                                    const float* __restrict__ p_step, const float* __restrict__ w_smp_t,
                                                    const float* __restrict__ smp_emb, const int* __restrict__ row_step,
-                                                   const int* __restrict__ row_prev, float* __restrict__ c,
-                                                   float* __restrict__ h, int row0, int n_rows, int H, int S, int t) {
+                                                   const int* __restrict__ row_prev, const int* __restrict__ row_trace,
+                                                   float* __restrict__ c, float* __restrict__ h, HImg himg, int row0,
+                                                   int n_rows, int H, int S, int t) {
   int64_t total = (int64_t)n_rows * H;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int i = (int)(e / H), j = (int)(e % H);
     int row = row0 + i;
     int st = row_step[row];
+    int tr = row_trace[row];
+    if (tr < 0) {  // padding row of a 128-row segment: keep every consumer's reduction clean
+      gates[(int64_t)row * 4 * H + j] = 0.f; gates[(int64_t)row * 4 * H + H + j] = 0.f;
+      gates[(int64_t)row * 4 * H + 2 * H + j] = 0.f; gates[(int64_t)row * 4 * H + 3 * H + j] = 0.f;
+      c[(int64_t)row * H + j] = 0.f; h[(int64_t)row * H + j] = 0.f;
+      if (himg.k_hi) tcg::img_store(himg.k_hi, himg.k_lo, himg.mn_hi, himg.mn_lo, row, j, himg.kb, 0.0f);
+      continue;
+    }
     float pre[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       int col = g * H + j;
-      float v = p_obs[(int64_t)i * 4 * H + col] + p_step[(int64_t)st * 4 * H + col];
+      float v = p_obs[(int64_t)tr * 4 * H + col] + p_step[(int64_t)st * 4 * H + col];
       if (t > 0) {
         v += gates[(int64_t)row * 4 * H + col];  // recurrent part written by the GEMM
         for (int s = 0; s < S; ++s) v = fmaf(smp_emb[(int64_t)row * S + s], w_smp_t[(int64_t)s * 4 * H + col], v);
@@ -352,6 +392,7 @@ __global__ void __launch_bounds__(256) k_cell_fwd(float* __restrict__ gates, con
     gates[(int64_t)row * 4 * H + 3 * H + j] = og;
     c[(int64_t)row * H + j] = cn;
     h[(int64_t)row * H + j] = hn;
+    if (himg.k_hi) tcg::img_store(himg.k_hi, himg.k_lo, himg.mn_hi, himg.mn_lo, row, j, himg.kb, hn);
   }
 }
 
@@ -360,12 +401,18 @@ __global__ void __launch_bounds__(128) k_head_nll(const float* __restrict__ out_
                                                    const ppb_addr_desc* __restrict__ addrs,
                                                    const int* __restrict__ row_step, const int* __restrict__ step_addr,
                                                    const float* __restrict__ values, const float* __restrict__ prior0,
-                                                   const float* __restrict__ prior1, int R, int K, float inv_batch,
-                                                   float* __restrict__ row_lp, float* __restrict__ d_out,
-                                                   float* __restrict__ loss_acc) {
+                                                   const float* __restrict__ prior1, const int* __restrict__ row_trace,
+                                                   int R, int K, float inv_batch, float* __restrict__ row_lp,
+                                                   float* __restrict__ d_out, HImg dimg, float* __restrict__ loss_acc) {
   float local = 0.0f;
   int bad = 0;
   for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < R; row += gridDim.x * blockDim.x) {
+    if (row_trace[row] < 0) {  // padding row
+      if (row_lp) row_lp[row] = 0.0f;
+      if (d_out) for (int j = 0; j < out_pad; ++j) d_out[(int64_t)row * out_pad + j] = 0.0f;
+      if (dimg.k_hi) for (int j = 0; j < (int)dimg.kb * 32; ++j) tcg::img_store(dimg.k_hi, dimg.k_lo, dimg.mn_hi, dimg.mn_lo, row, j, dimg.kb, 0.0f);
+      continue;
+    }
     const ppb_addr_desc& a = addrs[step_addr[row_step[row]]];
     const float* x = out_raw + (int64_t)row * out_pad;
     float xs[heads::CMAX > 3 * heads::KMAX ? heads::CMAX : 3 * heads::KMAX];
@@ -382,7 +429,10 @@ __global__ void __launch_bounds__(128) k_head_nll(const float* __restrict__ out_
     if (row_lp) row_lp[row] = lp;
     local += -lp;
     if (d_out)
-      for (int j = 0; j < O; ++j) d_out[(int64_t)row * out_pad + j] = gx[j] * inv_batch;
+      for (int j = 0; j < out_pad; ++j) d_out[(int64_t)row * out_pad + j] = j < O ? gx[j] * inv_batch : 0.0f;
+    if (dimg.k_hi)
+      for (int j = 0; j < (int)dimg.kb * 32; ++j)
+        tcg::img_store(dimg.k_hi, dimg.k_lo, dimg.mn_hi, dimg.mn_lo, row, j, dimg.kb, j < O ? gx[j] * inv_batch : 0.0f);
   }
   local = ppb_warp_sum(local);
   bad = __reduce_add_sync(0xffffffffu, bad);
@@ -406,27 +456,42 @@ __global__ void __launch_bounds__(256) k_cell_bwd(const float* __restrict__ gate
                                                    const float* __restrict__ dh, const float* __restrict__ dh_rec,
                                                    float* __restrict__ dc, float* __restrict__ dgates,
                                                    float* __restrict__ d_pobs, const int* __restrict__ row_prev,
-                                                   int row0, int n_rows, int n_next, int H, int t) {
+                                                   const int* __restrict__ row_next, const int* __restrict__ row_trace,
+                                                   HImg gimg, int row0, int n_rows, int H, int t) {
   int64_t total = (int64_t)n_rows * H;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int i = (int)(e / H), j = (int)(e % H);
     int row = row0 + i;
+    int tr = row_trace[row];
+    float* dgr = dgates + (int64_t)row * 4 * H;
+    if (tr < 0) {
+      dgr[j] = 0.f; dgr[H + j] = 0.f; dgr[2 * H + j] = 0.f; dgr[3 * H + j] = 0.f;
+      if (gimg.k_hi)
+        for (int g4 = 0; g4 < 4; ++g4) tcg::img_store(gimg.k_hi, gimg.k_lo, gimg.mn_hi, gimg.mn_lo, row, g4 * H + j, gimg.kb, 0.0f);
+      continue;
+    }
+    const int nx = row_next[row];
     const float* g = gates + (int64_t)row * 4 * H;
     float ig = g[j], fg = g[H + j], gg = g[2 * H + j], og = g[3 * H + j];
     float cn = c[(int64_t)row * H + j];
     float cp = (t > 0) ? c[(int64_t)row_prev[row] * H + j] : 0.0f;
     float tc = tanhf(cn);
-    bool has_next = i < n_next;
-    float dht = dh[(int64_t)row * H + j] + (has_next ? dh_rec[(int64_t)i * H + j] : 0.0f);
-    float dct = (has_next ? dc[(int64_t)i * H + j] : 0.0f) + dht * og * (1.0f - tc * tc);
+    bool has_next = nx >= 0;
+    float dht = dh[(int64_t)row * H + j] + (has_next ? dh_rec[(int64_t)row * H + j] : 0.0f);
+    float dct = (has_next ? dc[(int64_t)nx * H + j] : 0.0f) + dht * og * (1.0f - tc * tc);
     float di = dct * gg * ig * (1.0f - ig);
     float df = dct * cp * fg * (1.0f - fg);
     float dg = dct * ig * (1.0f - gg * gg);
     float d_o = dht * tc * og * (1.0f - og);
-    dc[(int64_t)i * H + j] = dct * fg;
-    float* dgr = dgates + (int64_t)row * 4 * H;
+    dc[(int64_t)row * H + j] = dct * fg;
     dgr[j] = di; dgr[H + j] = df; dgr[2 * H + j] = dg; dgr[3 * H + j] = d_o;
-    float* dp = d_pobs + (int64_t)i * 4 * H;
+    if (gimg.k_hi) {
+      tcg::img_store(gimg.k_hi, gimg.k_lo, gimg.mn_hi, gimg.mn_lo, row, j, gimg.kb, di);
+      tcg::img_store(gimg.k_hi, gimg.k_lo, gimg.mn_hi, gimg.mn_lo, row, H + j, gimg.kb, df);
+      tcg::img_store(gimg.k_hi, gimg.k_lo, gimg.mn_hi, gimg.mn_lo, row, 2 * H + j, gimg.kb, dg);
+      tcg::img_store(gimg.k_hi, gimg.k_lo, gimg.mn_hi, gimg.mn_lo, row, 3 * H + j, gimg.kb, d_o);
+    }
+    float* dp = d_pobs + (int64_t)tr * 4 * H;
     if (has_next) { dp[j] += di; dp[H + j] += df; dp[2 * H + j] += dg; dp[3 * H + j] += d_o; }
     else { dp[j] = di; dp[H + j] = df; dp[2 * H + j] = dg; dp[3 * H + j] = d_o; }
   }
@@ -567,6 +632,8 @@ int check_batch(const ppb_net* net, const ppb_batch* b) {
 
 }  // namespace
 
+#include "net_tc.inc"
+
 // =====================================================================================================
 extern "C" {
 
@@ -605,7 +672,7 @@ int ppb_net_set_tables(ppb_net* net, const ppb_addr_desc* addrs, int32_t n_addrs
   PPB_CUDA(cudaMalloc((void**)&net->d_type_off, sizeof(int64_t) * n_types));
   PPB_CUDA(cudaMemcpy(net->d_addrs, addrs, sizeof(ppb_addr_desc) * n_addrs, cudaMemcpyHostToDevice));
   PPB_CUDA(cudaMemcpy(net->d_type_off, type_off, sizeof(int64_t) * n_types, cudaMemcpyHostToDevice));
-  return PPB_OK;
+  return build_weight_images(net);
 }
 
 int ppb_net_destroy(ppb_net* net) {
@@ -615,7 +682,11 @@ int ppb_net_destroy(ppb_net* net) {
   for (int i = 0; i < 2; ++i) {
     if (net->h_stage[i]) cudaFreeHost(net->h_stage[i]);
     if (net->ev_stage[i]) cudaEventDestroy(net->ev_stage[i]);
+    if (net->h_blob[i]) cudaFreeHost(net->h_blob[i]);
+    if (net->ev_blob[i]) cudaEventDestroy(net->ev_blob[i]);
   }
+  if (net->wimg) cudaFree(net->wimg);
+  if (net->d_pack) cudaFree(net->d_pack);
   delete net;
   return PPB_OK;
 }
@@ -624,8 +695,8 @@ int64_t ppb_ic_workspace_bytes(const ppb_net* net, int32_t n_traces, int32_t n_r
                                int32_t n_groups) {
   if (!net || n_traces <= 0 || n_rows <= 0) return -1;
   Dims d; d.B = n_traces; d.R = n_rows; d.T = t_max; d.NS = n_steps; d.G = n_groups;
-  Ws w = carve(net, d, nullptr);
-  return w.total_bytes + dgates_bytes(net, d) + 1024;
+  // SIMT region (fp32 activations + dgates) followed by the tensor-core tail (tile images, problem lists)
+  return simt_region_bytes(net, d) + carve_tc(net, d, nullptr).total_bytes + 1024;
 }
 
 int ppb_ic_loss_forward(ppb_net* net, const float* arena, const ppb_batch* b, void* workspace,
@@ -635,11 +706,14 @@ int ppb_ic_loss_forward(ppb_net* net, const float* arena, const ppb_batch* b, vo
   if (rc) return rc;
   PPB_CHECK_ARG(arena && workspace, "null arena/workspace");
   PPB_CHECK_ARG(!net->addrs.empty(), "address tables not set");
-  (void)precision;
+  PPB_CHECK_ARG(precision >= 0 && precision <= 2, "unknown precision mode");
   const ppb_net_desc& D = net->desc;
   Dims d = dims_of(b);
   PPB_CHECK_ARG(workspace_bytes >= ppb_ic_workspace_bytes(net, d.B, d.R, d.T, d.NS, d.G), "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
+  if (precision != PPB_PREC_FP32_SIMT)
+    return tc_loss_forward(net, arena, b, workspace, precision, loss_out, status_out, row_lp_out, want_grad, st);
+  PPB_CHECK_ARG(b->row_align == 1, "the SIMT path needs a batch encoded with row_align = 1");
   Ws w = carve(net, d, workspace);
   const int H = D.lstm_dim, H4 = 4 * H, E = D.obs_dim, S = D.sample_dim, I = net->I;
   const int C2 = 2 * (D.type_dim + D.addr_dim);
@@ -700,15 +774,15 @@ int ppb_ic_loss_forward(ppb_net* net, const float* arena, const ppb_batch* b, vo
     int r0 = b->row_off_host[t], n = b->row_off_host[t + 1] - r0;
     if (t > 0) { rc = run_phase(bl.phases[ph_rec0 + t - 1], w.problems, st, &bl); if (rc) return rc; }
     k_cell_fwd<<<ew_grid((int64_t)n * H), 256, 0, st>>>(w.gates, w.p_obs, w.p_step, w.w_smp_t, w.smp_emb, b->row_step,
-                                                       b->row_prev, w.c, w.h, r0, n, H, S, t);
+                                                       b->row_prev, b->row_trace, w.c, w.h, HImg(), r0, n, H, S, t);
     PPB_LAUNCH_CHECK();
   }
   rc = run_phase(bl.phases[ph_h1], w.problems, st); if (rc) return rc;
   rc = run_phase(bl.phases[ph_h2], w.problems, st); if (rc) return rc;
   k_head_nll<<<ew_grid(d.R, 128), 128, 0, st>>>(w.out_raw, net->out_pad, net->d_addrs, b->row_step, b->step_addr,
-                                                b->values, b->prior0, b->prior1, d.R, D.mixture_k, 1.0f / (float)d.B,
-                                                row_lp_out ? row_lp_out : w.row_lp, want_grad ? w.d_out : nullptr,
-                                                w.loss_acc);
+                                                b->values, b->prior0, b->prior1, b->row_trace, d.R, D.mixture_k,
+                                                1.0f / (float)d.B, row_lp_out ? row_lp_out : w.row_lp,
+                                                want_grad ? w.d_out : nullptr, HImg(), w.loss_acc);
   PPB_LAUNCH_CHECK();
   k_publish_loss<<<1, 32, 0, st>>>(w.loss_acc, loss_out, status_out);
   PPB_LAUNCH_CHECK();
@@ -720,11 +794,11 @@ int ppb_ic_loss_backward(ppb_net* net, const float* arena, float* grad, const pp
   int rc = check_batch(net, b);
   if (rc) return rc;
   PPB_CHECK_ARG(arena && grad && workspace, "null arena/grad/workspace");
-  (void)precision;
   const ppb_net_desc& D = net->desc;
   Dims d = dims_of(b);
   PPB_CHECK_ARG(workspace_bytes >= ppb_ic_workspace_bytes(net, d.B, d.R, d.T, d.NS, d.G), "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
+  if (precision != PPB_PREC_FP32_SIMT) return tc_loss_backward(net, arena, grad, b, workspace, precision, grad_scale, st);
   Ws w = carve(net, d, workspace);
   float* dgates = dgates_ptr(w, workspace);
   const int H = D.lstm_dim, H4 = 4 * H, E = D.obs_dim, S = D.sample_dim, I = net->I;
@@ -766,7 +840,7 @@ int ppb_ic_loss_backward(ppb_net* net, const float* arena, float* grad, const pp
   for (int t = d.T - 1; t >= 1; --t) {
     bl.begin();
     int r0 = b->row_off_host[t], n = b->row_off_host[t + 1] - r0;
-    bl.add(linear_dx(dgates + (int64_t)r0 * H4, H4, arena + D.w_hh_off, H, w.dh_rec, H, n, H4, H, 0));
+    bl.add(linear_dx(dgates + (int64_t)r0 * H4, H4, arena + D.w_hh_off, H, w.dh_rec + (int64_t)b->row_off_host[t - 1] * H, H, n, H4, H, 0));
   }
   const int ph_lstm_w = (int)bl.phases.size();
   bl.begin();
@@ -848,7 +922,7 @@ int ppb_ic_loss_backward(ppb_net* net, const float* arena, float* grad, const pp
     int n_next = (t + 1 < d.T) ? b->row_off_host[t + 2] - b->row_off_host[t + 1] : 0;
     if (n_next > 0) { rc = run_phase(bl.phases[ph_rec0 + (d.T - 2 - t)], w.problems, st, &bl); if (rc) return rc; }
     k_cell_bwd<<<ew_grid((int64_t)n * H), 256, 0, st>>>(w.gates, w.c, w.dh, w.dh_rec, w.dc, dgates, w.d_pobs, b->row_prev,
-                                                       r0, n, n_next, H, t);
+                                                       b->row_next, b->row_trace, HImg(), r0, n, H, t);
     PPB_LAUNCH_CHECK();
   }
   {
@@ -1113,13 +1187,20 @@ int ppb_batch_from_image(const void* image_host, const void* image_dev, int64_t 
   out->n_traces = (int32_t)hd[1]; out->n_sub = (int32_t)hd[2]; out->t_max = (int32_t)hd[3];
   out->n_rows = (int32_t)hd[4]; out->n_steps = (int32_t)hd[5]; out->n_groups = (int32_t)hd[6];
   out->obs_in_total = (int32_t)hd[7];
-  for (int k = 9; k < 9 + 15; ++k)
+  for (int k = 9; k < 9 + 19; ++k)
     PPB_CHECK_ARG(hd[k] >= PPB_IMAGE_HEADER_WORDS * 8 && hd[k] < image_bytes && (hd[k] & 15) == 0, "bad array offset");
+  out->row_align = (int32_t)hd[28];
+  PPB_CHECK_ARG(out->row_align == 1 || out->row_align == 128, "row_align must be 1 or 128");
   const char* Hh = (const char*)image_host;
   const char* Dv = (const char*)image_dev;
   out->row_off_host = (const int32_t*)(Hh + hd[9]);
   out->group_addr_host = (const int32_t*)(Hh + hd[10]);
   out->group_start_host = (const int32_t*)(Hh + hd[11]);
+  out->step_addr_host = (const int32_t*)(Hh + hd[13]);
+  out->step_row0_host = (const int32_t*)(Hh + hd[15]);
+  out->step_nrows_host = (const int32_t*)(Hh + hd[16]);
+  out->step_t_host = (const int32_t*)(Hh + hd[26]);
+  out->step_prev_row0_host = (const int32_t*)(Hh + hd[27]);
   if (Dv) {
     out->trace_sub = (const int32_t*)(Dv + hd[12]);
     out->step_addr = (const int32_t*)(Dv + hd[13]);
@@ -1133,6 +1214,10 @@ int ppb_batch_from_image(const void* image_host, const void* image_dev, int64_t 
     out->prior1 = (const float*)(Dv + hd[21]);
     out->obs = (const float*)(Dv + hd[22]);
     out->head_rows = (const int32_t*)(Dv + hd[23]);
+    out->row_trace = (const int32_t*)(Dv + hd[24]);
+    out->row_next = (const int32_t*)(Dv + hd[25]);
+    out->step_t = (const int32_t*)(Dv + hd[26]);
+    out->step_prev_row0 = (const int32_t*)(Dv + hd[27]);
   }
   return PPB_OK;
 }

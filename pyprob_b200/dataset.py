@@ -82,7 +82,7 @@ class TraceBatch:
                 return np.stack([(zeros if c < 0 else host[c])[sel] for c in cs], axis=0)
             obs = np.stack([host[c][sel] for c in obs_cols], axis=1)
             subs.append(SubBatch(ids, rows(vc), rows(p0c), rows(p1c), obs))
-        self._encoded = EncodedBatch(subs)
+        self._encoded = EncodedBatch(subs, row_align=net.row_align)
         return self._encoded
 
 

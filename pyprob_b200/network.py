@@ -323,6 +323,11 @@ class InferenceNetworkLSTM(nn.Module):
             self._history_num_params_trace.append(self._total_train_traces)
         return changed
 
+    @property
+    def row_align(self):
+        """Row layout the native path expects: 128-row segments on the tensor cores, compact rows on the SIMT path."""
+        return 1 if self._precision == 2 else 128
+
     def num_parameters(self):
         return sum(int(np.prod(s)) for _, s in self.parameter_index.values())
 

@@ -66,7 +66,7 @@ class ArrayBatch:
                 ids = [net._addresses[a]['id'] for a in sb['addresses']]
                 subs.append(SubBatch(ids, np.asarray(sb['values']), np.asarray(sb['prior0']), np.asarray(sb['prior1']),
                                      np.asarray(sb['obs'])))
-            self._encoded = EncodedBatch(subs)
+            self._encoded = EncodedBatch(subs, row_align=net.row_align)
         return self._encoded
 
 
