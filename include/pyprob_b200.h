@@ -284,6 +284,13 @@ int ppb_adam_step(float* arena, const float* grad, float* exp_avg, float* exp_av
                   float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
                   float grad_scale, void* stream);
 
+/* Same update with the step counter and hyper-parameters in device memory, so that a whole training step
+ * (forward, backward, optimiser) can be captured once in a CUDA graph and replayed.
+ *   hyper_dev: float[6] = lr, beta1, beta2, eps, weight_decay, grad_scale
+ *   state_dev: 16 bytes: int64 step counter (incremented by the call), float bc1, float sqrt(bc2) */
+int ppb_adam_step_dev(float* arena, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      const float* hyper_dev, void* state_dev, void* stream);
+
 /* Batched proposal step for IC posterior sampling (inference_network_lstm.py:82-134 for n particles in
  * lock-step at the same address).  h/c: fp32[n,H] LSTM state, updated in place (zeros at t=0).
  * prev_addr < 0 means first step.  Writes the proposal parameters:

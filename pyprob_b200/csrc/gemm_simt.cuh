@@ -40,6 +40,7 @@ constexpr int BM = 64, BN = 64, BK = 16, kThreads = 256;
 __global__ void __launch_bounds__(kThreads) k_grouped(const Problem* __restrict__ probs, int n_probs, int total_tiles) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
+  __shared__ Problem sP;  // the descriptor is read hundreds of times per tile: keep it on chip
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     // binary search the owning problem
     int lo = 0, hi = n_probs - 1;
@@ -47,7 +48,11 @@ __global__ void __launch_bounds__(kThreads) k_grouped(const Problem* __restrict_
       int mid = (lo + hi + 1) >> 1;
       if (probs[mid].tile_start <= tile) lo = mid; else hi = mid - 1;
     }
-    const Problem& P = probs[lo];
+    __syncthreads();
+    for (int i = threadIdx.x; i < (int)(sizeof(Problem) / 4); i += blockDim.x)
+      reinterpret_cast<uint32_t*>(&sP)[i] = reinterpret_cast<const uint32_t*>(probs + lo)[i];
+    __syncthreads();
+    const Problem& P = sP;
     const int local = tile - P.tile_start;
     const int tm = local / P.tiles_n, tn = local % P.tiles_n;
     const int m0 = tm * BM, n0 = tn * BN;
@@ -64,7 +69,9 @@ __global__ void __launch_bounds__(kThreads) k_grouped(const Problem* __restrict_
     const bool a_k_fast = (P.sak == 1) || (P.ka_gather == nullptr && P.sak < P.sam);
     const bool b_k_fast = (P.sbk == 1) || (P.kb_gather == nullptr && P.sbk < P.sbn);
 
-    for (int k0 = 0; k0 < P.K; k0 += BK) {
+    // register-staged software pipeline: the global loads of chunk k+1 are in flight while chunk k is multiplied
+    float ra[4], rb[4];
+    auto fetch = [&](int k0) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         int e = tid + i * kThreads;  // 0..1023
@@ -77,22 +84,32 @@ __global__ void __launch_bounds__(kThreads) k_grouped(const Problem* __restrict_
           int64_t pk = P.ka_gather ? P.ka_gather[k] : k;
           v = __ldg(P.A + pm * P.sam + pk * P.sak);
         }
-        As[kk][mm] = v;
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        int e = tid + i * kThreads;
-        int nn, kk;
+        ra[i] = v;
+        int nn;
         if (b_k_fast) { kk = e % BK; nn = e / BK; } else { nn = e % BN; kk = e / BN; }
-        int n = n0 + nn, k = k0 + kk;
-        float v = 0.0f;
+        int n = n0 + nn;
+        k = k0 + kk;
+        v = 0.0f;
         if (n < P.N && k < P.K) {
           int64_t pk = P.kb_gather ? P.kb_gather[k] : k;
           v = __ldg(P.B + (int64_t)n * P.sbn + pk * P.sbk);
         }
-        Bs[kk][nn] = v;
+        rb[i] = v;
+      }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < P.K; k0 += BK) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int e = tid + i * kThreads;
+        int mm, kk, nn;
+        if (a_k_fast) { kk = e % BK; mm = e / BK; } else { mm = e % BM; kk = e / BM; }
+        As[kk][mm] = ra[i];
+        if (b_k_fast) { kk = e % BK; nn = e / BK; } else { nn = e % BN; kk = e / BN; }
+        Bs[kk][nn] = rb[i];
       }
       __syncthreads();
+      if (k0 + BK < P.K) fetch(k0 + BK);
 #pragma unroll
       for (int kk = 0; kk < BK; ++kk) {
         float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);

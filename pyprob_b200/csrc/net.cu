@@ -45,6 +45,10 @@ struct ppb_net {
   int pack_tiles = 0;
   WImg w_ihE, w_hh;
   std::vector<WImg> w1, w2;
+  // content hashes of the problem lists last uploaded to each device region: identical lists are not re-sent,
+  // which also makes a repeated step capturable in a CUDA graph (no host->device copy inside the capture)
+  uint64_t slot_hash[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const void* slot_dev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   void* h_blob[2] = {nullptr, nullptr};
   cudaEvent_t ev_blob[2] = {nullptr, nullptr};
   size_t blob_cap = 0;
@@ -135,7 +139,7 @@ Ws carve(const ppb_net* net, Dims d, void* base) {
   for (int j = 0; j < D.num_obs; ++j)
     for (int l = 0; l + 1 < D.obs_ff[j].num_layers; ++l) w.d_obs_act[j][l] = take((int64_t)d.B * D.obs_ff[j].layers[l].out_dim);
   // dgates reuses `gates`?  No: backward needs the activations; keep a separate buffer.
-  w.max_problems = 64 + 4LL * PPB_MAX_OBS * PPB_MAX_FF_LAYERS + 8LL * d.G + 4LL * d.T;
+  w.max_problems = 2 * (64 + 4LL * PPB_MAX_OBS * PPB_MAX_FF_LAYERS + 8LL * d.G + 4LL * d.T);  // fwd | bwd halves
   w.problems = (Problem*)take(w.max_problems * (int64_t)(sizeof(Problem) / 4));
   w.total_bytes = off;
   return w;
@@ -235,25 +239,48 @@ void add_obs_embed(Builder& bl, const ppb_net_desc& D, const float* arena, const
   }
 }
 
-int upload_and_get(ppb_net* net, const Builder& b, Problem* dev, int64_t cap, cudaStream_t st) {
+inline uint64_t fnv1a(const void* data, size_t n, uint64_t h = 1469598103934665603ULL) {
+  const unsigned char* p = (const unsigned char*)data;
+  for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ULL; }
+  return h;
+}
+
+// Send `bytes` of host data to `dev` through the pinned staging ring unless the same content already lives there.
+int upload_cached(ppb_net* net, int slot, const void* src, size_t bytes, void* dev, cudaStream_t st) {
+  if (bytes == 0) return PPB_OK;
+  uint64_t h = fnv1a(src, bytes, 1469598103934665603ULL ^ (uint64_t)bytes);
+  if (net->slot_hash[slot] == h && net->slot_dev[slot] == dev) return PPB_OK;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap);
+  if (cap != cudaStreamCaptureStatusNone) {
+    ppb_set_error("the batch structure changed inside a CUDA-graph capture: run the step once eagerly first");
+    return PPB_EINVAL;
+  }
+  if (net->blob_cap < bytes) {
+    for (int i = 0; i < 2; ++i) {
+      if (net->h_blob[i]) cudaFreeHost(net->h_blob[i]);
+      PPB_CUDA(cudaMallocHost(&net->h_blob[i], bytes * 2));
+      if (!net->ev_blob[i]) PPB_CUDA(cudaEventCreateWithFlags(&net->ev_blob[i], cudaEventDisableTiming));
+    }
+    net->blob_cap = bytes * 2;
+  }
+  int i = net->blob_idx;
+  net->blob_idx ^= 1;
+  PPB_CUDA(cudaEventSynchronize(net->ev_blob[i]));
+  memcpy(net->h_blob[i], src, bytes);
+  PPB_CUDA(cudaMemcpyAsync(dev, net->h_blob[i], bytes, cudaMemcpyHostToDevice, st));
+  PPB_CUDA(cudaEventRecord(net->ev_blob[i], st));
+  net->slot_hash[slot] = h;
+  net->slot_dev[slot] = dev;
+  return PPB_OK;
+}
+
+// slots: 0/1 SIMT forward/backward lists, 2/3 tensor-core forward/backward lists, 4 reduction-chunk lists,
+// 5 inference-time lists.  Forward and backward lists live in separate halves of the device region.
+int upload_and_get(ppb_net* net, const Builder& b, Problem* dev, int64_t cap, cudaStream_t st, int slot = 0) {
   size_t n = b.probs.size();
   if ((int64_t)n > cap) { ppb_set_error("problem list overflow (%zu > %lld)", n, (long long)cap); return PPB_ENOMEM; }
-  if (n == 0) return PPB_OK;
-  if (net->stage_cap < n) {
-    for (int i = 0; i < 2; ++i) {
-      if (net->h_stage[i]) cudaFreeHost(net->h_stage[i]);
-      PPB_CUDA(cudaMallocHost((void**)&net->h_stage[i], n * 2 * sizeof(Problem)));
-      if (!net->ev_stage[i]) PPB_CUDA(cudaEventCreateWithFlags(&net->ev_stage[i], cudaEventDisableTiming));
-    }
-    net->stage_cap = n * 2;
-  }
-  int i = net->stage_idx;
-  net->stage_idx ^= 1;
-  PPB_CUDA(cudaEventSynchronize(net->ev_stage[i]));
-  memcpy(net->h_stage[i], b.probs.data(), n * sizeof(Problem));
-  PPB_CUDA(cudaMemcpyAsync(dev, net->h_stage[i], n * sizeof(Problem), cudaMemcpyHostToDevice, st));
-  PPB_CUDA(cudaEventRecord(net->ev_stage[i], st));
-  return PPB_OK;
+  return upload_cached(net, slot, b.probs.data(), n * sizeof(Problem), dev, st);
 }
 
 // ---- optional kernel-level profiling of the LSTM gate GEMM class (bench.py roofline) ---------------
@@ -396,47 +423,158 @@ __global__ void __launch_bounds__(256) k_cell_fwd(float* __restrict__ gates, con
   }
 }
 
-// heads: family transform + log q(value) + d(-log q)/d out, loss reduction (:199-218)
-__global__ void __launch_bounds__(128) k_head_nll(const float* __restrict__ out_raw, int out_pad,
+// heads: family transform + log q(value) + d(-log q)/d out, loss reduction (:199-218).
+// One WARP per row: lane k owns mixture component k (or categories k, k+32, ...), reductions are shuffles;
+// the formulas are those of heads.cuh (mixture_nll / categorical_nll), restated lane-parallel.
+__global__ void __launch_bounds__(256) k_head_nll(const float* __restrict__ out_raw, int out_pad,
                                                    const ppb_addr_desc* __restrict__ addrs,
                                                    const int* __restrict__ row_step, const int* __restrict__ step_addr,
                                                    const float* __restrict__ values, const float* __restrict__ prior0,
                                                    const float* __restrict__ prior1, const int* __restrict__ row_trace,
                                                    int R, int K, float inv_batch, float* __restrict__ row_lp,
                                                    float* __restrict__ d_out, HImg dimg, float* __restrict__ loss_acc) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int img_cols = (int)dimg.kb * 32;
   float local = 0.0f;
   int bad = 0;
-  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < R; row += gridDim.x * blockDim.x) {
-    if (row_trace[row] < 0) {  // padding row
-      if (row_lp) row_lp[row] = 0.0f;
-      if (d_out) for (int j = 0; j < out_pad; ++j) d_out[(int64_t)row * out_pad + j] = 0.0f;
-      if (dimg.k_hi) for (int j = 0; j < (int)dimg.kb * 32; ++j) tcg::img_store(dimg.k_hi, dimg.k_lo, dimg.mn_hi, dimg.mn_lo, row, j, dimg.kb, 0.0f);
-      continue;
+  for (int row = warp; row < R; row += nwarps) {
+    const bool valid = row_trace[row] >= 0;
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;  // this lane's gradient entries (mixture: m,s,p ; categorical: 4 cats)
+    float lp = 0.0f;
+    int O = 0;
+    bool is_cat = false;
+    if (valid) {
+      const ppb_addr_desc a = addrs[step_addr[row_step[row]]];
+      const float* x = out_raw + (int64_t)row * out_pad;
+      const float v = values[row];
+      O = a.head_out;
+      is_cat = a.family == PPB_FAMILY_CATEGORICAL;
+      if (is_cat) {
+        const int C = a.num_categories;
+        float q[4], xs[4];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { int c = lane + 32 * i; xs[i] = c < C ? x[c] : -INFINITY; mx = fmaxf(mx, xs[i]); }
+        mx = ppb_warp_max(mx);
+        float s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { q[i] = (lane + 32 * i < C) ? expf(xs[i] - mx) : 0.0f; s += q[i]; }
+        s = ppb_warp_sum(s);
+        float S = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { q[i] = (lane + 32 * i < C) ? q[i] / s + PPB_UTIL_EPSILON : 0.0f; S += q[i]; }
+        S = ppb_warp_sum(S);
+        const int iv = (int)v;
+        if (iv < 0 || iv >= C) {
+          lp = NAN;
+        } else {
+          float qv = 0.0f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) if (lane + 32 * i == iv) qv = q[i];
+          qv = ppb_warp_sum(qv);
+          float ph = qv / S;
+          bool clamped = (ph < PPB_EPS32) || (ph > 1.0f - PPB_EPS32);
+          lp = logf(ppb_clamp_prob(ph));
+          if (!clamped && lp > -INFINITY) {
+            float dot = 0.0f, g[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              int c = lane + 32 * i;
+              g[i] = c < C ? ((c == iv) ? 1.0f / qv : 0.0f) - 1.0f / S : 0.0f;
+              dot += c < C ? (q[i] - PPB_UTIL_EPSILON) * g[i] : 0.0f;
+            }
+            dot = ppb_warp_sum(dot);
+            g0 = -((q[0] - PPB_UTIL_EPSILON) * (g[0] - dot));
+            g1 = (lane + 32 < C) ? -((q[1] - PPB_UTIL_EPSILON) * (g[1] - dot)) : 0.f;
+            g2 = (lane + 64 < C) ? -((q[2] - PPB_UTIL_EPSILON) * (g[2] - dot)) : 0.f;
+            g3 = (lane + 96 < C) ? -((q[3] - PPB_UTIL_EPSILON) * (g[3] - dot)) : 0.f;
+            if (lane >= C) g0 = 0.f;
+          }
+        }
+      } else {
+        const bool on = lane < K;
+        const int fam = a.family;
+        const float p0 = prior0[row], p1 = prior1[row];
+        const float xm = on ? x[lane] : 0.f, xsd = on ? x[K + lane] : 0.f, xp = on ? x[2 * K + lane] : -INFINITY;
+        float mx = ppb_warp_max(xp);
+        float e = on ? expf(xp - mx) : 0.0f;
+        float prob = e / ppb_warp_sum(e);
+        float mean, sd, lo = 0.f, hi = 0.f;
+        if (fam == PPB_FAMILY_NORMAL) { mean = p0 + xm * p1; sd = expf(xsd) * p1; }
+        else if (fam == PPB_FAMILY_UNIFORM) {
+          float range = p1 - p0;
+          mean = p0 + heads::sigmoidf_(xm) * range;
+          sd = range / 1000.0f + heads::sigmoidf_(xsd) * range * 10.0f;
+          lo = p0; hi = p1;
+        } else { mean = heads::sigmoidf_(xm) * 40.0f; sd = expf(xsd); lo = 0.f; hi = 40.f; }
+        const bool trunc = fam != PPB_FAMILY_NORMAL;
+        float S = ppb_warp_sum(on ? prob : 0.0f);
+        float ph = prob / S;
+        bool clamped = (ph < PPB_EPS32) || (ph > 1.0f - PPB_EPS32);
+        float lw = logf(ppb_clamp_prob(ph));
+        float lpk = trunc ? ppb_truncnormal_lp(v, mean, sd, lo, hi) : ppb_normal_lp(v, mean, sd);
+        float t = on ? lw + lpk : -INFINITY;
+        if (on && isnan(t)) t = NAN;
+        float mxt = ppb_warp_max(t);
+        // NaN anywhere poisons the row (reference: has_nan_or_inf on the log_prob)
+        bool any_nan = __any_sync(0xffffffffu, on && isnan(t));
+        if (any_nan) lp = NAN;
+        else if (mxt == -INFINITY) lp = -INFINITY;
+        else lp = mxt + logf(ppb_warp_sum(on ? expf(t - mxt) : 0.0f));
+        if (lp > -INFINITY && lp < INFINITY) {
+          float r = on ? expf(t - lp) : 0.0f;
+          float sum_r_unc = ppb_warp_sum((on && !clamped) ? r : 0.0f);
+          float direct = (on && !clamped) ? r / ph : 0.0f;
+          float g_prob = (direct - sum_r_unc) / S;
+          float dot = ppb_warp_sum(on ? prob * g_prob : 0.0f);
+          float z = (v - mean) / sd, dmu, dsd;
+          if (!trunc) { dmu = z / sd; dsd = (z * z - 1.0f) / sd; }
+          else {
+            float alpha = (lo - mean) / sd, beta = (hi - mean) / sd;
+            float Z = ppb_std_normal_cdf(beta) - ppb_std_normal_cdf(alpha);
+            float pa = heads::std_normal_pdf(alpha), pb = heads::std_normal_pdf(beta);
+            dmu = z / sd - (pa - pb) / (sd * Z);
+            dsd = (z * z - 1.0f) / sd - (alpha * pa - beta * pb) / (sd * Z);
+          }
+          dmu *= r; dsd *= r;
+          float dxm, dxs;
+          if (fam == PPB_FAMILY_NORMAL) { dxm = dmu * p1; dxs = dsd * sd; }
+          else if (fam == PPB_FAMILY_UNIFORM) {
+            float range = p1 - p0, sm = heads::sigmoidf_(xm), ss = heads::sigmoidf_(xsd);
+            dxm = dmu * sm * (1.0f - sm) * range;
+            dxs = dsd * ss * (1.0f - ss) * range * 10.0f;
+          } else { float sm = heads::sigmoidf_(xm); dxm = dmu * sm * (1.0f - sm) * 40.0f; dxs = dsd * sd; }
+          if (on) { g0 = -dxm; g1 = -dxs; g2 = -(prob * (g_prob - dot)); }
+        }
+      }
+      if (lp == -INFINITY) { lp = PPB_LOG_EPSILON; g0 = g1 = g2 = g3 = 0.f; }  // util.replace_negative_inf (:213)
+      if (isnan(lp) || isinf(lp)) { if (lane == 0) bad += 1; lp = 0.0f; g0 = g1 = g2 = g3 = 0.f; }
+      if (lane == 0) local += -lp;
     }
-    const ppb_addr_desc& a = addrs[step_addr[row_step[row]]];
-    const float* x = out_raw + (int64_t)row * out_pad;
-    float xs[heads::CMAX > 3 * heads::KMAX ? heads::CMAX : 3 * heads::KMAX];
-    float gx[heads::CMAX > 3 * heads::KMAX ? heads::CMAX : 3 * heads::KMAX];
-    int O = a.head_out;
-    for (int j = 0; j < O; ++j) xs[j] = x[j];
-    float lp;
-    if (a.family == PPB_FAMILY_CATEGORICAL)
-      lp = heads::categorical_nll(xs, a.num_categories, values[row], gx, d_out != nullptr);
-    else
-      lp = heads::mixture_nll(a.family, xs, K, prior0[row], prior1[row], values[row], gx, d_out != nullptr);
-    if (lp == -INFINITY) lp = PPB_LOG_EPSILON;       // util.replace_negative_inf (:213), zero gradient
-    if (isnan(lp) || isinf(lp)) { bad += 1; lp = 0.0f; for (int j = 0; j < O; ++j) gx[j] = 0.0f; }
-    if (row_lp) row_lp[row] = lp;
-    local += -lp;
-    if (d_out)
-      for (int j = 0; j < out_pad; ++j) d_out[(int64_t)row * out_pad + j] = j < O ? gx[j] * inv_batch : 0.0f;
-    if (dimg.k_hi)
-      for (int j = 0; j < (int)dimg.kb * 32; ++j)
-        tcg::img_store(dimg.k_hi, dimg.k_lo, dimg.mn_hi, dimg.mn_lo, row, j, dimg.kb, j < O ? gx[j] * inv_batch : 0.0f);
+    if (row_lp && lane == 0) row_lp[row] = lp;
+    // scatter this lane's entries; everything else in the (padded) row is zero
+    if (d_out) {
+      const int ncols = (dimg.k_hi && img_cols > out_pad) ? img_cols : out_pad;
+      auto put = [&](int j, float gv) {
+        gv *= inv_batch;
+        if (j < out_pad) d_out[(int64_t)row * out_pad + j] = gv;
+        if (dimg.k_hi && j < img_cols) tcg::img_store(dimg.k_hi, dimg.k_lo, dimg.mn_hi, dimg.mn_lo, row, j, dimg.kb, gv);
+      };
+      if (valid) {
+        if (is_cat) {
+          if (lane < O) put(lane, g0);
+          if (lane + 32 < O) put(lane + 32, g1);
+          if (lane + 64 < O) put(lane + 64, g2);
+          if (lane + 96 < O) put(lane + 96, g3);
+        } else if (lane < K) {
+          put(lane, g0); put(K + lane, g1); put(2 * K + lane, g2);
+        }
+      }
+      for (int j = (valid ? O : 0) + lane; j < ncols; j += 32) put(j, 0.0f);
+    }
   }
-  local = ppb_warp_sum(local);
-  bad = __reduce_add_sync(0xffffffffu, bad);
-  if ((threadIdx.x & 31) == 0) {
+  if (lane == 0) {
     if (local != 0.0f) atomicAdd(loss_acc, local * inv_batch);
     if (bad) atomicAdd(reinterpret_cast<int*>(loss_acc + 1), bad);
   }
@@ -498,14 +636,24 @@ __global__ void __launch_bounds__(256) k_cell_bwd(const float* __restrict__ gate
 }
 
 // d_pstep[st, col] = sum over the rows of step st (contiguous range) of dgates[row, col]
-__global__ void k_step_colsum(const float* __restrict__ dgates, const int* __restrict__ step_row0,
-                              const int* __restrict__ step_nrows, int H4, float* __restrict__ d_pstep) {
-  int st = blockIdx.y;
-  int r0 = step_row0[st], n = step_nrows[st];
-  for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < H4; col += gridDim.x * blockDim.x) {
-    float s = 0.0f;
-    for (int r = 0; r < n; ++r) s += dgates[(int64_t)(r0 + r) * H4 + col];
-    d_pstep[(int64_t)st * H4 + col] = s;
+__global__ void __launch_bounds__(256) k_step_colsum(const float* __restrict__ dgates, const int* __restrict__ step_row0,
+                                                      const int* __restrict__ step_nrows, int H4,
+                                                      float* __restrict__ d_pstep) {
+  __shared__ float part[8][33];
+  const int st = blockIdx.y;
+  const int r0 = step_row0[st], n = step_nrows[st];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  float s = 0.0f;
+  if (col < H4)
+    for (int r = slice; r < n; r += 8) s += dgates[(int64_t)(r0 + r) * H4 + col];
+  part[slice][lane] = s;
+  __syncthreads();
+  if (slice == 0 && col < H4) {
+    float t = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][lane];
+    d_pstep[(int64_t)st * H4 + col] = t;
   }
 }
 
@@ -587,16 +735,27 @@ __global__ void k_embed_scatter(const float* __restrict__ d_embcat, const ppb_ad
     else atomicAdd(grad + a.addr_emb_off + (jj - td), v);
   }
 }
-// bias gradient of a Linear: db[n] += sum_m dY[gm(m), n]
-__global__ void k_colsum_gather(const float* __restrict__ dY, int64_t ld, const int* __restrict__ m_gather, int M,
-                                int N, float* __restrict__ db) {
-  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
-    float s = 0.0f;
-    for (int m = 0; m < M; ++m) {
+// bias gradient of a Linear: db[n] += sum_m dY[gm(m), n].  Block = 32 columns x 8 row-slices; rows are
+// strided over the slices and blockIdx.y, partial sums meet in shared memory / one atomic per block column.
+__global__ void __launch_bounds__(256) k_colsum_gather(const float* __restrict__ dY, int64_t ld,
+                                                        const int* __restrict__ m_gather, int M, int N,
+                                                        float* __restrict__ db) {
+  __shared__ float part[8][33];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + lane;
+  float s = 0.0f;
+  if (n < N)
+    for (int m = blockIdx.y * 8 + slice; m < M; m += 8 * gridDim.y) {
       int64_t pm = m_gather ? m_gather[m] : m;
       s += dY[pm * ld + n];
     }
-    db[n] += s;
+  part[slice][lane] = s;
+  __syncthreads();
+  if (slice == 0 && n < N) {
+    float t = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][lane];
+    if (t != 0.0f) atomicAdd(db + n, t);
   }
 }
 __global__ void k_scale(float* __restrict__ x, int64_t n, float a) {
@@ -751,7 +910,7 @@ int ppb_ic_loss_forward(ppb_net* net, const float* arena, const ppb_batch* b, vo
     p.m_gather = b->head_rows + s0;
     bl.add(p);
   }
-  rc = upload_and_get(net, bl, w.problems, w.max_problems, st);
+  rc = upload_and_get(net, bl, w.problems, w.max_problems / 2, st, 0);
   if (rc) return rc;
 
   // ---- launches -----------------------------------------------------------------------------------
@@ -779,7 +938,7 @@ int ppb_ic_loss_forward(ppb_net* net, const float* arena, const ppb_batch* b, vo
   }
   rc = run_phase(bl.phases[ph_h1], w.problems, st); if (rc) return rc;
   rc = run_phase(bl.phases[ph_h2], w.problems, st); if (rc) return rc;
-  k_head_nll<<<ew_grid(d.R, 128), 128, 0, st>>>(w.out_raw, net->out_pad, net->d_addrs, b->row_step, b->step_addr,
+  k_head_nll<<<ew_grid((int64_t)d.R * 32, 256), 256, 0, st>>>(w.out_raw, net->out_pad, net->d_addrs, b->row_step, b->step_addr,
                                                 b->values, b->prior0, b->prior1, b->row_trace, d.R, D.mixture_k,
                                                 1.0f / (float)d.B, row_lp_out ? row_lp_out : w.row_lp,
                                                 want_grad ? w.d_out : nullptr, HImg(), w.loss_acc);
@@ -901,36 +1060,37 @@ int ppb_ic_loss_backward(ppb_net* net, const float* arena, float* grad, const pp
       }
     }
   }
-  rc = upload_and_get(net, bl, w.problems, w.max_problems, st);
+  Problem* dprobs = w.problems + w.max_problems / 2;
+  rc = upload_and_get(net, bl, dprobs, w.max_problems / 2, st, 1);
   if (rc) return rc;
 
   // ---- launches -----------------------------------------------------------------------------------
-  rc = run_phase(bl.phases[ph_dhid], w.problems, st); if (rc) return rc;
-  rc = run_phase(bl.phases[ph_hw], w.problems, st); if (rc) return rc;
+  rc = run_phase(bl.phases[ph_dhid], dprobs, st); if (rc) return rc;
+  rc = run_phase(bl.phases[ph_hw], dprobs, st); if (rc) return rc;
   // head bias gradients
   for (int g = 0; g < d.G; ++g) {
     const ppb_addr_desc& a = net->addrs[b->group_addr_host[g]];
     int s0 = b->group_start_host[g], cnt = b->group_start_host[g + 1] - s0;
-    k_colsum_gather<<<(a.head_out + 127) / 128, 128, 0, st>>>(w.d_out, net->out_pad, b->head_rows + s0, cnt, a.head_out, grad + a.b2_off);
+    k_colsum_gather<<<dim3((a.head_out + 31) / 32, 8), 256, 0, st>>>(w.d_out, net->out_pad, b->head_rows + s0, cnt, a.head_out, grad + a.b2_off);
     PPB_LAUNCH_CHECK();
-    k_colsum_gather<<<(a.head_hidden + 127) / 128, 128, 0, st>>>(w.d_hid, net->dh_pad, b->head_rows + s0, cnt, a.head_hidden, grad + a.b1_off);
+    k_colsum_gather<<<dim3((a.head_hidden + 31) / 32, 8), 256, 0, st>>>(w.d_hid, net->dh_pad, b->head_rows + s0, cnt, a.head_hidden, grad + a.b1_off);
     PPB_LAUNCH_CHECK();
   }
   // BPTT
   for (int t = d.T - 1; t >= 0; --t) {
     int r0 = b->row_off_host[t], n = b->row_off_host[t + 1] - r0;
     int n_next = (t + 1 < d.T) ? b->row_off_host[t + 2] - b->row_off_host[t + 1] : 0;
-    if (n_next > 0) { rc = run_phase(bl.phases[ph_rec0 + (d.T - 2 - t)], w.problems, st, &bl); if (rc) return rc; }
+    if (n_next > 0) { rc = run_phase(bl.phases[ph_rec0 + (d.T - 2 - t)], dprobs, st, &bl); if (rc) return rc; }
     k_cell_bwd<<<ew_grid((int64_t)n * H), 256, 0, st>>>(w.gates, w.c, w.dh, w.dh_rec, w.dc, dgates, w.d_pobs, b->row_prev,
                                                        b->row_next, b->row_trace, HImg(), r0, n, H, t);
     PPB_LAUNCH_CHECK();
   }
   {
-    dim3 g((H4 + 255) / 256, d.NS);
+    dim3 g((H4 + 31) / 32, d.NS);
     k_step_colsum<<<g, 256, 0, st>>>(dgates, b->step_row0, b->step_nrows, H4, w.d_pstep);
     PPB_LAUNCH_CHECK();
   }
-  rc = run_phase(bl.phases[ph_lstm_w], w.problems, st, &bl); if (rc) return rc;
+  rc = run_phase(bl.phases[ph_lstm_w], dprobs, st, &bl); if (rc) return rc;
   k_bias_grad<<<(H4 + 255) / 256, 256, 0, st>>>(w.d_pstep, d.NS, H4, grad + D.b_ih_off, grad + D.b_hh_off);
   PPB_LAUNCH_CHECK();
   k_embed_scatter<<<ew_grid((int64_t)d.NS * C2), 256, 0, st>>>(w.d_embcat, net->d_addrs, net->d_type_off, b->step_addr,
@@ -952,9 +1112,9 @@ int ppb_ic_loss_backward(ppb_net* net, const float* arena, float* grad, const pp
     int l = D.obs_final.num_layers - 1 - (int)k;
     const ppb_linear_desc& L = D.obs_final.layers[l];
     float* dY = (l == D.obs_final.num_layers - 1) ? w.d_obs_emb : w.d_fin_act[l];
-    k_colsum_gather<<<(L.out_dim + 127) / 128, 128, 0, st>>>(dY, L.out_dim, nullptr, d.B, L.out_dim, grad + L.b_off);
+    k_colsum_gather<<<dim3((L.out_dim + 31) / 32, 8), 256, 0, st>>>(dY, L.out_dim, nullptr, d.B, L.out_dim, grad + L.b_off);
     PPB_LAUNCH_CHECK();
-    rc = run_phase(bl.phases[ph_fin[k]], w.problems, st); if (rc) return rc;
+    rc = run_phase(bl.phases[ph_fin[k]], dprobs, st); if (rc) return rc;
   }
   for (size_t k = 0; k < ph_obs.size(); ++k) {
     int l = max_depth - 1 - (int)k;
@@ -965,10 +1125,10 @@ int ppb_ic_loss_backward(ppb_net* net, const float* arena, float* grad, const pp
       bool last = (l == ff.num_layers - 1);
       const float* dY = last ? w.d_obs_cat + out_off[j] : w.d_obs_act[j][l];
       int64_t lddy = last ? E : L.out_dim;
-      k_colsum_gather<<<(L.out_dim + 127) / 128, 128, 0, st>>>(dY, lddy, nullptr, d.B, L.out_dim, grad + L.b_off);
+      k_colsum_gather<<<dim3((L.out_dim + 31) / 32, 8), 256, 0, st>>>(dY, lddy, nullptr, d.B, L.out_dim, grad + L.b_off);
       PPB_LAUNCH_CHECK();
     }
-    rc = run_phase(bl.phases[ph_obs[k]], w.problems, st); if (rc) return rc;
+    rc = run_phase(bl.phases[ph_obs[k]], dprobs, st); if (rc) return rc;
   }
   return PPB_OK;
 }
@@ -1006,6 +1166,28 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
   }
   for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
+    float gr = g[i] * gscale + wd * p[i];
+    float mi = b1 * m[i] + (1.0f - b1) * gr;
+    float vi = b2 * v[i] + (1.0f - b2) * gr * gr;
+    m[i] = mi; v[i] = vi;
+    p[i] -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  }
+}
+
+__global__ void k_adam_tick(const float* __restrict__ hyper, long long* __restrict__ step, float* __restrict__ bc) {
+  if (threadIdx.x == 0) {
+    long long t = *step + 1;
+    *step = t;
+    bc[0] = (float)(1.0 - pow((double)hyper[1], (double)t));
+    bc[1] = (float)sqrt(1.0 - pow((double)hyper[2], (double)t));
+  }
+}
+__global__ void __launch_bounds__(256) k_adam_dev(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                   const float* __restrict__ hyper, const float* __restrict__ bc) {
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], gscale = hyper[5];
+  const float step = lr / bc[0], bc2_sqrt = bc[1];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float gr = g[i] * gscale + wd * p[i];
     float mi = b1 * m[i] + (1.0f - b1) * gr;
     float vi = b2 * v[i] + (1.0f - b2) * gr * gr;
@@ -1233,6 +1415,21 @@ int ppb_adam_step(float* arena, const float* grad, float* exp_avg, float* exp_av
   return PPB_OK;
 }
 
+// Graph-replayable Adam: the step counter and the hyper-parameters live in device memory, so a captured
+// training step stays valid while the count advances and the learning rate follows its schedule.
+//   state_dev: int64 step counter at [0], then float bias corrections at byte offset 8 (bc1, sqrt(bc2))
+//   hyper_dev: float[6] = lr, beta1, beta2, eps, weight_decay, grad_scale
+int ppb_adam_step_dev(float* arena, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      const float* hyper_dev, void* state_dev, void* stream) {
+  PPB_CHECK_ARG(arena && grad && exp_avg && exp_avg_sq && hyper_dev && state_dev && n > 0, "bad arguments");
+  k_adam_tick<<<1, 32, 0, (cudaStream_t)stream>>>(hyper_dev, (long long*)state_dev, (float*)((char*)state_dev + 8));
+  PPB_LAUNCH_CHECK();
+  k_adam_dev<<<ppb_grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(arena, grad, exp_avg, exp_avg_sq, n, hyper_dev,
+                                                                       (const float*)((char*)state_dev + 8));
+  PPB_LAUNCH_CHECK();
+  return PPB_OK;
+}
+
 int64_t ppb_ic_infer_workspace_bytes(const ppb_net* net, int64_t n) {
   if (!net || n <= 0) return -1;
   return carve_infer(net, n, nullptr).total_bytes + 1024;
@@ -1246,7 +1443,7 @@ int ppb_ic_embed_observe(ppb_net* net, const float* arena, const float* obs, flo
   InferWs w = carve_infer(net, n, workspace);
   Builder bl;
   add_obs_embed(bl, net->desc, arena, obs, (int)n, w.obs_act, w.obs_cat, w.fin_act, obs_emb_out);
-  int rc = upload_and_get(net, bl, w.problems, w.max_problems, st);
+  int rc = upload_and_get(net, bl, w.problems, w.max_problems, st, 5);
   if (rc) return rc;
   for (auto& ph : bl.phases) { rc = run_phase(ph, w.problems, st); if (rc) return rc; }
   return PPB_OK;
@@ -1286,7 +1483,7 @@ int ppb_ic_infer_step(ppb_net* net, const float* arena, const float* obs_emb, in
   bl.begin();
   bl.add(linear_fwd(w.hid, net->dh_pad, arena + cur.w2_off, cur.head_hidden, arena + cur.b2_off, w.out_raw, net->out_pad,
                     (int)n, cur.head_out, cur.head_hidden, 0));
-  int rc = upload_and_get(net, bl, w.problems, w.max_problems, st);
+  int rc = upload_and_get(net, bl, w.problems, w.max_problems, st, 5);
   if (rc) return rc;
   k_step_row_infer<<<1, 128, 0, st>>>(arena, prev, first ? 0 : 1, cur, net->d_type_off, D.type_dim, D.addr_dim, w.emb_row);
   PPB_LAUNCH_CHECK();

@@ -24,6 +24,8 @@ enum : int {
   kMaskImg = 4,     // result = mask_img(m, n) > 0 ? result : 0   (mask image: K-format hi part, output geometry)
   kZeroInvalid = 8, // rows m >= m_valid produce zeros (padding rows of a segment)
 };
+// Split-K: when k_splits > 1 the reduction is divided over k_splits CTAs per output tile and the fp32 result
+// is combined with atomicAdd (the caller zero-initialises / accumulates into C; no images, bias or mask).
 
 struct Operand {
   const float* hi;
@@ -49,7 +51,7 @@ struct Problem {
   int o_kb;           // column blocks of the output / mask images
   int o_row0, o_col0; // origin of C(0,0) inside the output images (mult of 128 / 32)
   int tile_start, tiles_m, tiles_n;
-  int pad_;
+  int k_splits;
 };
 
 constexpr int kStages = 3;
@@ -67,6 +69,7 @@ struct __align__(1024) Smem {
   uint64_t empty[kStages];
   uint64_t tmem_full;
   uint32_t tmem_base;
+  Problem prob;  // on-chip copy of the descriptor
 };
 
 __device__ __forceinline__ uint32_t stage_bytes(const Operand& o, int tile_idx) {
@@ -112,10 +115,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_grouped(const Problem* __restri
     int mid = (lo_i + hi_i + 1) >> 1;
     if (probs[mid].tile_start <= tile) lo_i = mid; else hi_i = mid - 1;
   }
-  const Problem& P = probs[lo_i];
+  for (int i = threadIdx.x; i < (int)(sizeof(Problem) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(&sm.prob)[i] = reinterpret_cast<const uint32_t*>(probs + lo_i)[i];
+  __syncthreads();
+  const Problem& P = sm.prob;
   const int local = tile - P.tile_start;
-  const int mt = local / P.tiles_n, nt = local % P.tiles_n;
+  const int tiles_mn = P.tiles_m * P.tiles_n;
+  const int split = local / tiles_mn, rem = local % tiles_mn;
+  const int mt = rem / P.tiles_n, nt = rem % P.tiles_n;
   const int KC = (P.K + 31) / 32;
+  const int nsplit = P.k_splits > 1 ? P.k_splits : 1;
+  const int c0 = (int)((int64_t)KC * split / nsplit), c1 = (int)((int64_t)KC * (split + 1) / nsplit);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
@@ -131,9 +141,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_grouped(const Problem* __restri
   if (warp == 0) {
     if (lane == 0) {
       const uint32_t bytes = (stage_bytes(P.a, mt) + stage_bytes(P.b, nt)) * (X3 ? 2u : 1u);
-      for (int c = 0; c < KC; ++c) {
-        int s = c % kStages;
-        uint32_t ph = (c / kStages) & 1;
+      for (int c = c0; c < c1; ++c) {
+        int s = (c - c0) % kStages;
+        uint32_t ph = ((c - c0) / kStages) & 1;
         mbar_wait(&sm.empty[s], ph ^ 1);
         mbar_expect_tx(&sm.full[s], bytes);
         load_operand(P.a, mt, c, sm.a_hi[s], sm.a_lo[s], X3, &sm.full[s]);
@@ -144,9 +154,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_grouped(const Problem* __restri
     if (lane == 0) {
       const uint32_t idesc = idesc_tf32(128, kBN, P.a.mn, P.b.mn);
       const bool amn = P.a.mn != 0, bmn = P.b.mn != 0;
-      for (int c = 0; c < KC; ++c) {
-        int s = c % kStages;
-        uint32_t ph = (c / kStages) & 1;
+      for (int c = c0; c < c1; ++c) {
+        int s = (c - c0) % kStages;
+        uint32_t ph = ((c - c0) / kStages) & 1;
         mbar_wait(&sm.full[s], ph);
         fence_after_sync();
         uint32_t sa_hi = smem_u32(sm.a_hi[s]), sa_lo = smem_u32(sm.a_lo[s]);
@@ -157,11 +167,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_grouped(const Problem* __restri
           if (X3) {
             uint64_t al = operand_desc(amn, sa_lo, ks), bl = operand_desc(bmn, sb_lo, ks);
             // three accumulators (see tc_gemm.cu): cross terms, hi*hi of even chunks, hi*hi of odd chunks
-            mma_tf32(tmem + 2 * kBN, al, bh, idesc, (c == 0 && ks == 0) ? 0u : 1u);
+            mma_tf32(tmem + 2 * kBN, al, bh, idesc, (c == c0 && ks == 0) ? 0u : 1u);
             mma_tf32(tmem + 2 * kBN, ah, bl, idesc, 1u);
-            mma_tf32(tmem + (c & 1) * kBN, ah, bh, idesc, (c < 2 && ks == 0) ? 0u : 1u);
+            mma_tf32(tmem + (c & 1) * kBN, ah, bh, idesc, (c - c0 < 2 && ks == 0) ? 0u : 1u);
           } else {
-            mma_tf32(tmem, ah, bh, idesc, (c == 0 && ks == 0) ? 0u : 1u);
+            mma_tf32(tmem, ah, bh, idesc, (c == c0 && ks == 0) ? 0u : 1u);
           }
         }
         mma_commit(&sm.empty[s]);
@@ -180,11 +190,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_grouped(const Problem* __restri
       const int n0 = nt * kBN + cb * 32;
       if (n0 >= ((P.N + 31) & ~31)) break;  // warp-uniform
       float v[32];
-      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + cb * 32, v);
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (X3 ? (c0 & 1) * kBN : 0) + cb * 32, v);
       if (X3) {
         float u[32];
-        if (KC > 1) {
-          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + kBN + cb * 32, u);
+        if (c1 - c0 > 1) {
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ((c0 & 1) ^ 1) * kBN + cb * 32, u);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += u[j];
         }
@@ -217,7 +227,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_grouped(const Problem* __restri
       }
       if (P.c && row_ok) {
         float* crow = P.c + (int64_t)m * P.ldc;
-        if (P.flags & kAccumulate) {
+        if (nsplit > 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (n0 + j < P.N && v[j] != 0.0f) atomicAdd(crow + n0 + j, v[j]);
+        } else if (P.flags & kAccumulate) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (n0 + j < P.N) crow[n0 + j] += v[j];
         } else {

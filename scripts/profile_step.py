@@ -1,0 +1,51 @@
+"""Per-kernel device times of the bench training step in a normal (non-ncu) run, via CUPTI (torch.profiler)."""
+import os, sys, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from pyprob_b200 import _lib, synthetic
+from pyprob_b200._lib import call, ptr
+from pyprob_b200.util import Optimizer
+from pyprob_b200.network import BatchStruct
+
+prec = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+cfg = sys.argv[2] if len(sys.argv) > 2 else 'gum'
+B = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+dev = torch.device('cuda:0')
+rng = np.random.default_rng(0)
+if cfg == 'gum':
+    net = synthetic.gum_network(lstm_dim=512, precision=prec); batch = synthetic.gum_batch(rng, B)
+else:
+    T = int(cfg[1:]) if cfg.startswith('s') and len(cfg) > 1 else 50
+    net = synthetic.synthetic50_network(precision=prec, T=T); batch = synthetic.synthetic50_batch(rng, B, T=T)
+net._optimizer_type, net._learning_rate_init, net._weight_decay = Optimizer.ADAM, 1e-3, 0.0
+net._create_optimizer(); net._sync_native()
+enc = batch.encode(net)
+grad = torch.zeros_like(net._arena.data); net._arena.grad = grad
+img = torch.from_numpy(enc.pack().copy()).pin_memory(); dimg = img.to(dev)
+bs = BatchStruct(); call('ppb_batch_from_image', img.data_ptr(), dimg.data_ptr(), img.numel(), C.byref(bs))
+need = net._ensure_workspace(enc)
+st = torch.cuda.current_stream().cuda_stream
+loss = torch.empty((), device=dev); status = torch.zeros(1, dtype=torch.int32, device=dev)
+n = [0]
+def step():
+    grad.zero_()
+    call('ppb_ic_loss_forward', net._handle, ptr(net._arena.data), C.byref(bs), ptr(net._workspace), need, prec, ptr(loss), ptr(status), None, 1, st)
+    call('ppb_ic_loss_backward', net._handle, ptr(net._arena.data), ptr(grad), C.byref(bs), ptr(net._workspace), need, prec, 1.0, st)
+    n[0] += 1
+    call('ppb_adam_step', ptr(net._arena.data), ptr(grad), ptr(net._exp_avg), ptr(net._exp_avg_sq), net._arena.numel(), 1e-3, 0.9, 0.999, 1e-8, 0.0, n[0], 1.0, st)
+for _ in range(5): step()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(50): step()
+e1.record(); torch.cuda.synchronize()
+print('avg step (no L2 flush, back-to-back): %.1f us  | rows %d params %d' % (e0.elapsed_time(e1) * 1000 / 50, enc.n_rows, net._arena.numel()))
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    for _ in range(5): step()
+    torch.cuda.synchronize()
+rows = [(e.key[:70], e.count, e.device_time_total / max(e.count, 1), e.device_time_total) for e in prof.key_averages() if e.device_time_total > 0]
+tot = sum(r[3] for r in rows)
+for k, c, avg, t in sorted(rows, key=lambda r: -r[3])[:25]:
+    print('%-72s n=%4d avg=%8.1f us total=%9.1f us %5.1f%%' % (k, c, avg, t, 100 * t / tot))
+print('device total per step: %.1f us' % (tot / 5))
