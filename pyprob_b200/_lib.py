@@ -65,6 +65,7 @@ _SIGNATURES = {
     'ppb_packed_floats': [c_i64, c_i64],
     'ppb_pack_tf32': [c_f, c_i64, c_i64, c_i64, c_f, c_f, c_f],
     'ppb_pack_tf32_mn': [c_f, c_i64, c_i64, c_i64, c_f, c_f, c_f],
+    'ppb_debug_trace': [c_f],
     'ppb_gemm_packed_tn': [c_f, c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_int, c_f],
     'ppb_gemm_packed': [c_f, c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_f, c_int, c_int, c_f],
 }

@@ -8,7 +8,8 @@
 // so forward GEMMs, input-gradient GEMMs and weight-gradient GEMMs all read the same row-major tensors
 // without transposed copies (a tensor that is read both ways keeps one image per format).
 // One pipeline stage = 32 reduction elements: a 16 KB tile (K-major) or 4 x 4 KB row pieces (MN-major).
-// Warp roles (192 threads): warp 0 bulk-TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-5 epilogue.
+// Warp roles (576 threads): warp 0 bulk-TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-17 epilogue
+// (a lone warp per scheduler issues ~0.2 instr/clk on dependent code; 16 warps hide that latency).
 // One 128 x 128 output tile per CTA.
 #pragma once
 #include "common.cuh"
@@ -17,6 +18,11 @@
 namespace tcg {
 
 using namespace tc;
+
+// explicit global-space accesses: pointers fetched from the on-chip descriptor are generic to the compiler
+__device__ __forceinline__ void st_global(float* p, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ void red_add_global(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ float ld_global(const float* p) { float v; asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v; }
 
 enum : int {
   kRelu = 1,        // max(x, 0)
@@ -55,7 +61,8 @@ struct Problem {
 };
 
 constexpr int kStages = 3;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 16;                     // 4 TMEM lane quadrants x 4 column chunks: one 32 x 32 block per warp
+constexpr int kThreads = 64 + 32 * kEpiWarps;     // + bulk-TMA producer warp + MMA/TMEM warp
 constexpr int kBN = 128;
 constexpr int kTmemCols = 512;
 constexpr int kPiece = 32 * 128;  // bytes: 32 rows x 128 B
@@ -71,6 +78,9 @@ struct __align__(1024) Smem {
   uint32_t tmem_base;
   Problem prob;  // on-chip copy of the descriptor
 };
+// The epilogue warps transpose their blocks through the operand stages, which are idle once the last MMA has
+// completed (16 warps x 32 x 33 floats = 66 KB <= the 96 KB of a_hi + a_lo).
+static_assert(kEpiWarps * 32 * 33 * 4 <= 2 * kStages * kTileBytes, "transpose buffers must fit in the A stages");
 
 __device__ __forceinline__ uint32_t stage_bytes(const Operand& o, int tile_idx) {
   if (!o.mn) return kTileBytes;
@@ -104,8 +114,20 @@ __device__ __forceinline__ uint64_t operand_desc(bool mn, uint32_t smem_addr, in
   return mn ? smem_desc_sw128_mn(smem_addr + ks * 1024, kPiece, 512) : smem_desc_sw128(smem_addr) + (uint64_t)(ks * 2);
 }
 
-template <bool X3>
-__global__ void __launch_bounds__(kThreads, 1) k_grouped(const Problem* __restrict__ probs, int n_probs) {
+// EPI selects the (compile-time) epilogue flavour so that the row loop is straight-line code:
+//   0 = fp32 store (+bias, relu)   1 = fp32 reduction (red.add: weight gradients, split-K)   2 = tile images (+fp32)
+template <bool X3, int EPI>
+__global__ void __launch_bounds__(kThreads, 1) k_grouped(const Problem* __restrict__ probs, int n_probs,
+                                                          unsigned long long* __restrict__ trace) {
+#define TCG_TRACE(slot)                                                                                   \
+  do {                                                                                                    \
+    if (trace && blockIdx.x == 0) {                                                                       \
+      unsigned long long _t;                                                                              \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                                              \
+      trace[slot] = _t;                                                                                   \
+    }                                                                                                     \
+  } while (0)
+  if (threadIdx.x == 0) TCG_TRACE(0);
   extern __shared__ uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -137,6 +159,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_grouped(const Problem* __restri
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = sm.tmem_base;
+  if (threadIdx.x == 0) TCG_TRACE(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -158,6 +181,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_grouped(const Problem* __restri
         int s = (c - c0) % kStages;
         uint32_t ph = ((c - c0) / kStages) & 1;
         mbar_wait(&sm.full[s], ph);
+        if (c == c0) TCG_TRACE(2);
         fence_after_sync();
         uint32_t sa_hi = smem_u32(sm.a_hi[s]), sa_lo = smem_u32(sm.a_lo[s]);
         uint32_t sb_hi = smem_u32(sm.b_hi[s]), sb_lo = smem_u32(sm.b_lo[s]);
@@ -177,18 +201,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_grouped(const Problem* __restri
         mma_commit(&sm.empty[s]);
       }
       mma_commit(&sm.tmem_full);
+      TCG_TRACE(3);
     }
   } else {
-    const int q = warp & 3;
+    // Epilogue.  TMEM hands each thread one ROW (32 consecutive columns per load); writing rows straight out would
+    // scatter every store instruction over 32 cache lines (measured: 8.7 us per tile).  Each warp therefore
+    // transposes its 32 x 32 block through shared memory and emits whole 128-byte row spans: lane = column.
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int cb = (warp - 2) >> 2;         // its 32-column chunk of the 128-column tile
+    float (*stg)[33] = reinterpret_cast<float (*)[33]>(reinterpret_cast<float*>(sm.a_hi) + (warp - 2) * 32 * 33);
     mbar_wait(&sm.tmem_full, 0);
+    if (threadIdx.x == 64) TCG_TRACE(4);
     fence_after_sync();
-    const int m = mt * 128 + q * 32 + lane;  // row of C handled by this thread
-    const bool row_ok = m < P.M;
-    const bool row_valid = row_ok && (!(P.flags & kZeroInvalid) || m < P.m_valid);
-#pragma unroll 1
-    for (int cb = 0; cb < kBN / 32; ++cb) {
+    const int m_base = mt * 128 + q * 32;  // first row of C handled by this warp
+    // hoist everything that does not depend on the row out of the (fully unrolled) row loop
+    const bool do_relu = (P.flags & kRelu) != 0, do_mask = (P.flags & kMaskImg) != 0;
+    const int rows = (P.M - m_base) < 32 ? (P.M - m_base) : 32;
+    const int valid_rows = (P.flags & kZeroInvalid) ? (P.m_valid - m_base) : 32;
+    const float* bias_p = P.bias;
+    const float* mask_p = P.mask_hi;
+    float* c_p = P.c;
+    float* ok_hi = P.o_k_hi; float* ok_lo = P.o_k_lo; float* omn_hi = P.o_mn_hi; float* omn_lo = P.o_mn_lo;
+    const int64_t ldc = P.ldc, o_kb = P.o_kb, orow0 = (int64_t)P.o_row0 + m_base, ocb0 = P.o_col0 / 32 + nt * 4;
+    {
       const int n0 = nt * kBN + cb * 32;
-      if (n0 >= ((P.N + 31) & ~31)) break;  // warp-uniform
+      if (n0 < ((P.N + 31) & ~31) && m_base < P.M) {  // warp-uniform
       float v[32];
       tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (X3 ? (c0 & 1) * kBN : 0) + cb * 32, v);
       if (X3) {
@@ -202,75 +239,54 @@ __global__ void __launch_bounds__(kThreads, 1) k_grouped(const Problem* __restri
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += u[j];
       }
-      // image coordinates of this thread's 32-column span
-      const int64_t orow = (int64_t)P.o_row0 + m, ocb = P.o_col0 / 32 + nt * 4 + cb;
-      const int64_t tile_off = ((orow >> 7) * P.o_kb + ocb) * kTileFloats + (orow & 127) * 32;
-      const int rr = (int)(orow & 7), r3 = (int)(orow & 3);
+      __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        int n = n0 + j;
-        float x = v[j];
-        if (P.bias && n < P.N) x += __ldg(P.bias + n);
-        if (P.flags & kRelu) x = fmaxf(x, 0.0f);
-        if (!row_valid || n >= P.N) x = 0.0f;
-        v[j] = x;
-      }
-      if ((P.flags & kMaskImg) && row_ok) {
+      for (int j = 0; j < 32; ++j) stg[lane][j] = v[j];
+      __syncwarp();
+      const int n = n0 + lane;
+      const bool col_ok = n < P.N;
+      const float bias = (bias_p && col_ok) ? __ldg(bias_p + n) : 0.0f;
+      // the warp's 32 rows sit inside one 128-row image tile (m_base % 32 == 0, o_row0 % 128 == 0): row r of the block is
+      // image row (orow0 + r), so (orow & 7) == (r & 7) and the span offset advances by 32 floats per row
+      const int64_t span0 = ((orow0 >> 7) * o_kb + (ocb0 + cb)) * kTileFloats + (orow0 & 127) * 32;
+      float* cp = c_p ? c_p + (int64_t)m_base * ldc + n : nullptr;
+      const bool c_ok = cp != nullptr && col_ok;
 #pragma unroll
-        for (int c16 = 0; c16 < 8; ++c16) {
-          float4 mk = *reinterpret_cast<const float4*>(P.mask_hi + tile_off + ((c16 ^ rr) << 2));
-          if (!(mk.x > 0.0f)) v[c16 * 4 + 0] = 0.0f;
-          if (!(mk.y > 0.0f)) v[c16 * 4 + 1] = 0.0f;
-          if (!(mk.z > 0.0f)) v[c16 * 4 + 2] = 0.0f;
-          if (!(mk.w > 0.0f)) v[c16 * 4 + 3] = 0.0f;
-        }
-      }
-      if (P.c && row_ok) {
-        float* crow = P.c + (int64_t)m * P.ldc;
-        if (nsplit > 1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (n0 + j < P.N && v[j] != 0.0f) atomicAdd(crow + n0 + j, v[j]);
-        } else if (P.flags & kAccumulate) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (n0 + j < P.N) crow[n0 + j] += v[j];
+      for (int r = 0; r < 32; ++r) {
+        float x = stg[r][lane] + bias;
+        x = do_relu ? fmaxf(x, 0.0f) : x;
+        const bool live = r < rows;                        // row exists in C
+        x = (col_ok && r < valid_rows) ? x : 0.0f;
+        if (EPI == 0) {
+          if (live && c_ok) st_global(cp + (int64_t)r * ldc, x);
+        } else if (EPI == 1) {
+          if (live && c_ok && x != 0.0f) red_add_global(cp + (int64_t)r * ldc, x);
         } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (n0 + j < P.N) crow[n0 + j] = v[j];
+          const int64_t pos_k = span0 + r * 32 + ((((lane >> 2) ^ (r & 7))) << 2) + (lane & 3);
+          if (do_mask && live) x = (ld_global(mask_p + pos_k) > 0.0f) ? x : 0.0f;
+          if (live && c_ok) st_global(cp + (int64_t)r * ldc, x);
+          float h, l;
+          split_tf32(x, h, l);
+          if (live && ok_hi) { st_global(ok_hi + pos_k, h); st_global(ok_lo + pos_k, l); }
+          if (live && omn_hi) {
+            const int64_t pos_mn = span0 + r * 32 + ((((lane >> 3) ^ (r & 3))) << 3) + (lane & 7);
+            st_global(omn_hi + pos_mn, h);
+            st_global(omn_lo + pos_mn, l);
+          }
         }
       }
-      if ((P.o_k_hi || P.o_mn_hi) && row_ok) {
-        float h[32], l[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) split_tf32(v[j], h[j], l[j]);
-        if (P.o_k_hi) {
-#pragma unroll
-          for (int c16 = 0; c16 < 8; ++c16) {
-            int64_t o = tile_off + ((c16 ^ rr) << 2);
-            *reinterpret_cast<float4*>(P.o_k_hi + o) = make_float4(h[c16 * 4], h[c16 * 4 + 1], h[c16 * 4 + 2], h[c16 * 4 + 3]);
-            if (P.o_k_lo) *reinterpret_cast<float4*>(P.o_k_lo + o) = make_float4(l[c16 * 4], l[c16 * 4 + 1], l[c16 * 4 + 2], l[c16 * 4 + 3]);
-          }
-        }
-        if (P.o_mn_hi) {
-#pragma unroll
-          for (int c32 = 0; c32 < 4; ++c32) {
-            int64_t o = tile_off + ((c32 ^ r3) << 3);
-            *reinterpret_cast<float4*>(P.o_mn_hi + o) = make_float4(h[c32 * 8], h[c32 * 8 + 1], h[c32 * 8 + 2], h[c32 * 8 + 3]);
-            *reinterpret_cast<float4*>(P.o_mn_hi + o + 4) = make_float4(h[c32 * 8 + 4], h[c32 * 8 + 5], h[c32 * 8 + 6], h[c32 * 8 + 7]);
-            if (P.o_mn_lo) {
-              *reinterpret_cast<float4*>(P.o_mn_lo + o) = make_float4(l[c32 * 8], l[c32 * 8 + 1], l[c32 * 8 + 2], l[c32 * 8 + 3]);
-              *reinterpret_cast<float4*>(P.o_mn_lo + o + 4) = make_float4(l[c32 * 8 + 4], l[c32 * 8 + 5], l[c32 * 8 + 6], l[c32 * 8 + 7]);
-            }
-          }
-        }
       }
     }
   }
+  if (threadIdx.x == 64) TCG_TRACE(5);
   fence_before_sync();
   __syncthreads();
+  if (threadIdx.x == 0) TCG_TRACE(6);
   if (warp == 1) {
     fence_after_sync();
     tmem_dealloc<kTmemCols>(tmem);
   }
+  if (threadIdx.x == 0 && trace && blockIdx.x == 0) { trace[8] = (unsigned long long)P.M; trace[9] = (unsigned long long)P.N; trace[10] = (unsigned long long)P.K; trace[11] = (unsigned long long)gridDim.x; trace[12] = (unsigned long long)(c1 - c0); }
 }
 
 inline size_t smem_bytes() { return sizeof(Smem) + 1024; }

@@ -32,3 +32,19 @@ for (M, N, R) in [(2048, 64, 256), (271, 512, 256), (2048, 512, 4096)]:
     print('TN M%5d N%5d R%5d prec0: %8.1f us' % (M, N, R, t))
 t = timeit(lambda: torch.empty(1, device=dev).zero_())
 print('torch tiny kernel launch: %.1f us' % t)
+
+# device-side durations (CUPTI) of the bring-up kernel for tiny problems: the fixed cost of one tcgen05 tile
+from torch.profiler import profile, ProfilerActivity
+for (M, N, K) in [(128, 128, 32), (128, 128, 128), (128, 128, 512), (256, 2048, 64)]:
+    a = torch.randn(M, K, device=dev); b = torch.randn(N, K, device=dev); c = torch.empty(M, N, device=dev)
+    ah, al = pack(a); bh, bl = pack(b)
+    for _ in range(3):
+        call('ppb_gemm_packed', ptr(ah), ptr(al), ptr(bh), ptr(bl), ptr(c), M, N, K, N, None, 0, 0, stream())
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(20):
+            call('ppb_gemm_packed', ptr(ah), ptr(al), ptr(bh), ptr(bl), ptr(c), M, N, K, N, None, 0, 0, stream())
+        torch.cuda.synchronize()
+    for e in prof.key_averages():
+        if 'gemm_packed' in e.key:
+            print('device time M%d N%d K%d x3: %.2f us' % (M, N, K, e.device_time_total / e.count))
