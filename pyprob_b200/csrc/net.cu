@@ -16,6 +16,7 @@
 #include "gemm_simt.cuh"
 #include "heads.cuh"
 #include "tc_grouped.cuh"
+#include "obs_mlp.cuh"
 
 using gemm::Problem;
 
