@@ -351,6 +351,8 @@ def main():
         cpu_baseline, _ = cpu_reference_arm(10 ** 6, 2, budget_s=15.0)
         if not args.no_extra:
             extra = posterior_extras(dev)
+            extra['scoring_hbm_roofline'] = scoring_rooflines(dev, peaks)
+            extra['hbm_peak_gbs'] = peaks['hbm_gbs']
     if rank == 0:
         out = {'metric': 'ic_train_traces_per_sec', 'value': value, 'unit': 'traces/s', 'n_gpus': world,
                'steps': args.steps, 'warmup': warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
@@ -367,6 +369,57 @@ def main():
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def scoring_rooflines(dev, peaks):
+    """HBM roofline of the scoring / sampling / normalisation kernels at a saturating size (2^24 particles,
+    per-particle parameters: every operand array is 64 MiB, the working set is far beyond the 126 MB L2).
+    achieved = algorithmic bytes per particle x N / CUDA-event time."""
+    from pyprob_b200 import ops
+    n, K, C = 1 << 24, 10, 8
+    g = torch.Generator(device=dev).manual_seed(0)
+    v = torch.randn(n, device=dev, generator=g)
+    mu = torch.randn(n, device=dev, generator=g)
+    sd = torch.rand(n, device=dev, generator=g) + 0.5
+    lo = mu - 2.0
+    hi = mu + 2.0
+    rate = sd * 4
+    cnt = torch.poisson(rate, generator=g)
+    probs = torch.rand(n, C, device=dev, generator=g) + 0.01
+    cat = torch.randint(0, C, (n,), device=dev, generator=g).float()
+    m = torch.randn(n, K, device=dev, generator=g)
+    s = torch.rand(n, K, device=dev, generator=g) + 0.1
+    p = torch.rand(n, K, device=dev, generator=g) + 0.01
+    lw = torch.randn(n, device=dev, generator=g) * 5 - 40
+    out = torch.empty(n, device=dev)
+    cases = [
+        ('normal_log_prob', 16, lambda: ops.normal_log_prob(v, mu, sd, lp_out=out)),
+        ('uniform_log_prob', 16, lambda: ops.uniform_log_prob(v, lo, hi, lp_out=out)),
+        ('poisson_log_prob', 12, lambda: ops.poisson_log_prob(cnt, rate, lp_out=out)),
+        ('categorical_log_prob', 4 * C + 8, lambda: ops.categorical_log_prob(cat, probs, lp_out=out)),
+        ('mixture_normal_log_prob', (3 * K + 2) * 4, lambda: ops.mixture_normal_log_prob(v, m, s, p, lp_out=out)),
+        ('mixture_truncated_normal_log_prob', (3 * K + 4) * 4,
+         lambda: ops.mixture_truncated_normal_log_prob(v, m, s, p, lo, hi, lp_out=out)),
+        ('normal_sample', 12, lambda: ops.normal_sample(mu, sd, n, 1, 2)),
+        ('weights_finalize', 16, lambda: ops.weights_finalize(lw)),
+    ]
+    res = []
+    for name, bytes_per, fn in cases:
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        reps = 10
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        gbs = bytes_per * n / (ms * 1e-3) / 1e9
+        res.append({'kernel': name, 'bytes_per_particle': bytes_per, 'particles': n, 'ms': ms, 'achieved_gbs': gbs,
+                    'frac_of_hbm': gbs / peaks['hbm_gbs']})
+    return res
 
 
 def posterior_extras(dev):

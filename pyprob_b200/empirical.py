@@ -11,8 +11,11 @@ from . import ops
 
 
 class Empirical:
-    def __init__(self, values=None, log_weights=None, name='Empirical'):
+    def __init__(self, values=None, log_weights=None, name='Empirical', sharded=False):
+        """sharded=True: this rank holds one shard of the particles; normalisation statistics (log normaliser, ESS,
+        logits) are global — the per-block partial triples of all ranks are all-gathered and combined exactly."""
         self.name = name
+        self._sharded = sharded
         self._values = values                  # tensor [N, ...] on the GPU, or a python list
         n = len(values) if values is not None else 0
         if log_weights is None:
@@ -25,7 +28,11 @@ class Empirical:
     def finalize(self):
         self._length = int(self.log_weights.numel())
         if self._length > 0:
-            self._stats, self._logits = ops.weights_finalize(self.log_weights)
+            partials = None
+            if getattr(self, '_sharded', False):
+                from . import parallel
+                partials = parallel.gather_weight_partials(ops.weights_partials(self.log_weights))
+            self._stats, self._logits = ops.weights_finalize(self.log_weights, partials=partials)
         else:
             self._stats, self._logits = None, None
         self._probs = None

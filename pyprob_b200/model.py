@@ -52,10 +52,18 @@ class Model:
 
     def _traces(self, num_traces=10, trace_mode=TraceMode.PRIOR, prior_inflation=PriorInflation.DISABLED,
                 inference_engine=InferenceEngine.IMPORTANCE_SAMPLING, inference_network=None, map_func=None,
-                observe=None, likelihood_importance=1.0, batch_size=None, first_index=0, *args, **kwargs):
-        """Importance-sampling driver (reference: model.py:47-88) -> Empirical of map_func(trace) values."""
+                observe=None, likelihood_importance=1.0, batch_size=None, first_index=0, sharded=False, *args,
+                **kwargs):
+        """Importance-sampling driver (reference: model.py:47-88) -> Empirical of map_func(trace) values.
+
+        sharded=True (with torch.distributed initialised): `num_traces` is the GLOBAL particle count, this rank
+        draws its contiguous index range of the Philox stream and the returned Empirical is normalised globally."""
         if map_func is None:
             map_func = trace_result
+        if sharded:
+            from . import parallel
+            world, rank = parallel.world_info()
+            first_index, num_traces = parallel.shard_range(num_traces, rank, world)
         chunk = batch_size or min(num_traces, 1 << 20)
         if self._scalar_mode:
             chunk = 1
@@ -92,7 +100,7 @@ class Model:
             warnings.warn('Encountered {} trace(s) with nan, inf, or -inf log_weight. Discarding.'.format(nbad))
             keep = bad == 0
             vals, log_w = vals[keep], log_w[keep]
-        return Empirical(vals, log_w)
+        return Empirical(vals, log_w, sharded=sharded)
 
     # ---- public API -------------------------------------------------------------------------------------------
     def prior(self, num_traces=10, prior_inflation=PriorInflation.DISABLED, map_func=None, *args, **kwargs):

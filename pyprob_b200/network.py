@@ -21,7 +21,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import _lib, util
+from . import _lib, parallel, util
 from ._lib import call, ptr, stream
 from .encoding import EncodedBatch
 from .util import InferenceNetwork as InferenceNetworkType  # noqa: F401
@@ -569,17 +569,8 @@ class InferenceNetworkLSTM(nn.Module):
                     return
                 continue
             loss.backward()
-            if world > 1:
-                # one NCCL all-reduce over the flat gradient arena, loss scalar piggy-backed
-                self._arena.grad[0:0]  # noqa: B018 (keeps the flat layout explicit)
-                packed = torch.cat([self._arena.grad, loss.detach().view(1)])
-                dist.all_reduce(packed)
-                self._arena.grad.copy_(packed[:-1])
-                loss_value = float(packed[-1]) / world
-                grad_scale = 1.0 / world
-            else:
-                loss_value = float(loss.detach())
-                grad_scale = 1.0
+            # one all-reduce over the flat gradient arena, loss scalar piggy-backed
+            loss_value, grad_scale = parallel.allreduce_grad_and_loss(self._arena.grad, loss.detach())
             self._learning_rate = self._current_learning_rate()
             self.optimizer_step(grad_scale)
             if self._loss_init is None:
