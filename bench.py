@@ -244,9 +244,9 @@ def main():
     for i in range(warmup):
         device_step(i)
     barrier()
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = not args.no_graph
     graphs = []
-    if use_graph:  # the whole step replays from one CUDA graph per resident batch
+    if use_graph:  # the whole step (incl. the NCCL all-reduce for N > 1) replays from one CUDA graph per resident batch
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -328,12 +328,15 @@ def main():
     # ---- roofline of the gate-GEMM class: per-launch durations from CUDA events inside the step ---------------
     peaks = measured_peaks()
     roof = None
+    # every rank runs the profiled steps (the step contains the collective); only rank 0 records and reports
     if rank == 0:
         call('ppb_prof_enable', 1)
-        for i in range(min(args.steps, 20)):
-            flush.zero_()
-            device_step(i)
-        torch.cuda.synchronize()
+    prof_steps = min(args.steps, 20)
+    for i in range(prof_steps):
+        flush.zero_()
+        device_step(i)
+    torch.cuda.synchronize()
+    if rank == 0:
         ms, n, fl = C.c_double(), C.c_int64(), C.c_double()
         call('ppb_prof_read', C.byref(ms), C.byref(n), C.byref(fl))
         call('ppb_prof_enable', 0)
@@ -342,7 +345,7 @@ def main():
         roof = {'bound': 'tensor', 'kernel': 'LSTM gate GEMM class (P_obs/P_step/recurrent + their dX/dW)',
                 'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': achieved / tf32_peak,
                 'traffic': None, 'launches': n.value, 'avg_launch_us': ms.value * 1e3 / max(n.value, 1),
-                'flops_per_step': fl.value / max(min(args.steps, 20), 1),
+                'flops_per_step': fl.value / max(prof_steps, 1),
                 'peak_source': '{} bf16_tflops_sustained / 2 (tf32)'.format(peaks['source'])}
 
     extra = {}
@@ -367,8 +370,15 @@ def main():
                'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu_baseline,
                'extra': extra}
         print(json.dumps(out))
+        sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        # captured graphs keep NCCL work objects alive: drop them, drain, and leave without tearing the
+        # communicator down (destroy_process_group can block on graph-owned resources)
+        graphs.clear()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def scoring_rooflines(dev, peaks):
@@ -451,7 +461,101 @@ def posterior_extras(dev):
             ess = post.effective_sample_size  # device->host read of the result
         torch.cuda.synchronize()
         out['is_posterior_particles_per_sec_n{}'.format(n)] = reps * n / (time.perf_counter() - t0)
+    out.update(ic_posterior_extra())
+    out.update(synthetic50_extra(dev))
     return out
+
+
+def ic_posterior_extra():
+    """BASELINE configs[2] shape: GaussianUnknownMeanMarsaglia (stochastic control flow), IC posterior with 64k
+    particles through Model.posterior_results (lock-step while_loop; LSTM h=512).  Throughput does not depend on
+    how well the proposals are trained, so the network is only trained long enough to create its layers."""
+    import math
+    import pyprob_b200 as pyprob
+    from pyprob_b200 import InferenceEngine, InferenceNetwork, Model
+    from pyprob_b200.distributions import Normal, Uniform
+
+    class Marsaglia(Model):
+        def forward(self):
+            def body(s):
+                x = pyprob.sample(Uniform(-1, 1))
+                y = pyprob.sample(Uniform(-1, 1))
+                return {'x': x, 'y': y, 's': x * x + y * y}
+            st = pyprob.while_loop(lambda s: s['s'] >= 1, body, {'x': 0.0, 'y': 0.0, 's': 2.0})
+            mu = 1 + math.sqrt(5) * (st['x'] * torch.sqrt(-2 * torch.log(st['s']) / st['s']))
+            lik = Normal(mu, math.sqrt(2))
+            pyprob.observe(lik, name='obs0')
+            pyprob.observe(lik, name='obs1')
+            return mu
+    pyprob.seed(3)
+    pyprob.set_verbosity(0)
+    m = Marsaglia()
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.learn_inference_network(num_traces=20 * 1024, batch_size=1024, inference_network=InferenceNetwork.LSTM,
+                                  lstm_dim=512, observe_embeddings={'obs0': {'dim': 32}, 'obs1': {'dim': 32}})
+    n = 65536
+    m.posterior_results(n, InferenceEngine.IMPORTANCE_SAMPLING_WITH_INFERENCE_NETWORK, observe={'obs0': 8, 'obs1': 9})
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        post = m.posterior_results(n, InferenceEngine.IMPORTANCE_SAMPLING_WITH_INFERENCE_NETWORK,
+                                   observe={'obs0': 8, 'obs1': 9})
+        _ = post.effective_sample_size
+    torch.cuda.synchronize()
+    return {'ic_posterior_marsaglia_particles_per_sec_n65536': reps * n / (time.perf_counter() - t0),
+            'ic_posterior_marsaglia_addresses': len(m._inference_network._addresses)}
+
+
+def synthetic50_extra(dev, B=512, T=50):
+    """BASELINE configs[3] shape on one GPU: 50-address Normal/Categorical(4) model, LSTM h=512, obs dim 256,
+    512 traces per GPU (the per-GPU share of the 4096-trace global batch on 8 GPUs): device-resident train step."""
+    import ctypes as C
+    from pyprob_b200 import synthetic
+    from pyprob_b200._lib import call, ptr
+    from pyprob_b200.network import BatchStruct
+    from pyprob_b200.util import Optimizer
+    rng = np.random.default_rng(5)
+    net = synthetic.synthetic50_network(precision=0, T=T)
+    net._optimizer_type, net._learning_rate_init, net._weight_decay = Optimizer.ADAM, 1e-3, 0.0
+    net._create_optimizer()
+    net._sync_native()
+    enc = synthetic.synthetic50_batch(rng, B, T=T).encode(net)
+    grad = torch.zeros_like(net._arena.data)
+    img = torch.from_numpy(enc.pack().copy()).pin_memory()
+    dimg = img.to(dev)
+    bs = BatchStruct()
+    call('ppb_batch_from_image', img.data_ptr(), dimg.data_ptr(), img.numel(), C.byref(bs))
+    need = net._ensure_workspace(enc)
+    loss = torch.empty((), device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 0.0, 1.0], dtype=torch.float32, device=dev)
+    state = torch.zeros(4, dtype=torch.int32, device=dev)
+
+    def step():
+        st = torch.cuda.current_stream().cuda_stream
+        grad.zero_()
+        call('ppb_ic_loss_forward', net._handle, ptr(net._arena.data), C.byref(bs), ptr(net._workspace), need, 0, ptr(loss),
+             ptr(status), None, 1, st)
+        call('ppb_ic_loss_backward', net._handle, ptr(net._arena.data), ptr(grad), C.byref(bs), ptr(net._workspace), need, 0,
+             1.0, st)
+        call('ppb_adam_step_dev', ptr(net._arena.data), ptr(grad), ptr(net._exp_avg), ptr(net._exp_avg_sq),
+             net._arena.numel(), ptr(hyper), ptr(state), st)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 10
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {'synthetic50_train_traces_per_sec_b512': B / (ms * 1e-3), 'synthetic50_ms_per_step_b512': ms,
+            'synthetic50_parameters': int(net._arena.numel())}
 
 
 if __name__ == '__main__':
