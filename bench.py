@@ -355,6 +355,7 @@ def main():
         if not args.no_extra:
             extra = posterior_extras(dev)
             extra['scoring_hbm_roofline'] = scoring_rooflines(dev, peaks)
+            extra['gate_gemm_saturating_4096x2048x512'] = gate_gemm_saturating(dev, peaks)
             extra['hbm_peak_gbs'] = peaks['hbm_gbs']
     if rank == 0:
         out = {'metric': 'ic_train_traces_per_sec', 'value': value, 'unit': 'traces/s', 'n_gpus': world,
@@ -430,6 +431,45 @@ def scoring_rooflines(dev, peaks):
         res.append({'kernel': name, 'bytes_per_particle': bytes_per, 'particles': n, 'ms': ms, 'achieved_gbs': gbs,
                     'frac_of_hbm': gbs / peaks['hbm_gbs']})
     return res
+
+
+def gate_gemm_saturating(dev, peaks):
+    """The LSTM gate GEMM shape at a saturating batch (one recurrent step of 4096 traces: [4096,512] x [512,2048]^T)
+    through the production tcgen05 kernel: achieved tensor throughput vs the tf32 roofline."""
+    from pyprob_b200 import _lib
+    from pyprob_b200._lib import call, ptr, stream
+    M, N, K = 4096, 2048, 512
+    a = torch.randn(M, K, device=dev)
+    b = torch.randn(N, K, device=dev)
+    c = torch.empty(M, N, device=dev)
+
+    def pack(x):
+        nfl = _lib.call('ppb_packed_floats', x.shape[0], x.shape[1])
+        hi = torch.empty(nfl, device=dev)
+        lo = torch.empty(nfl, device=dev)
+        call('ppb_pack_tf32', ptr(x), x.shape[0], x.shape[1], x.stride(0), ptr(hi), ptr(lo), stream())
+        return hi, lo
+    ah, al = pack(a)
+    bh, bl = pack(b)
+    out = {}
+    for prec, name in ((0, '3xTF32'), (1, 'TF32')):
+        for _ in range(5):
+            call('ppb_gemm_packed', ptr(ah), ptr(al), ptr(bh), ptr(bl), ptr(c), M, N, K, N, None, 0, prec, stream())
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        reps = 20
+        for _ in range(reps):
+            call('ppb_gemm_packed', ptr(ah), ptr(al), ptr(bh), ptr(bl), ptr(c), M, N, K, N, None, 0, prec, stream())
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        useful = 2.0 * M * N * K / (ms * 1e-3) / 1e12
+        issued = useful * (3 if prec == 0 else 1)
+        peak = peaks['bf16_tflops'] / 2.0
+        out[name] = {'ms': ms, 'useful_tflops': useful, 'issued_tf32_tflops': issued, 'tf32_peak': peak,
+                     'frac_issued': issued / peak}
+    return out
 
 
 def posterior_extras(dev):

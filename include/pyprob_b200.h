@@ -335,7 +335,8 @@ int ppb_gemm_packed(const float* A_hi, const float* A_lo, const float* B_hi, con
                     float* C, int64_t M, int64_t N, int64_t K, int64_t ldc, const float* bias,
                     int relu, int precision, void* stream);
 
-/* Bring-up instrumentation of ppb_gemm_packed (device timestamps of its phases); NULL disables. */
+/* Phase-trace buffer for the tensor-core grouped GEMM: 64 launches x 16 int64 slots of globaltimer stamps written by
+ * CTA 0 of each launch (setup, first data, last MMA commit, accumulators ready, epilogue done); NULL disables. */
 int ppb_debug_trace(void* buf16_dev);
 /* TN form over the same images: C[M,N] = sum_r X[r,m] * Y[r,n], X packed from [R,M], Y from [R,N]
  * (both operands MN-major; used by every weight-gradient GEMM: no transposed copies in HBM). */
