@@ -501,6 +501,25 @@ def posterior_extras(dev):
             ess = post.effective_sample_size  # device->host read of the result
         torch.cuda.synchronize()
         out['is_posterior_particles_per_sec_n{}'.format(n)] = reps * n / (time.perf_counter() - t0)
+    # north_star's posterior case: GaussianUnknownMean, IC engine (LSTM h=512), 64k particles
+    import contextlib
+    import io
+    from pyprob_b200 import InferenceNetwork
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.learn_inference_network(num_traces=10 * 256, batch_size=256, inference_network=InferenceNetwork.LSTM,
+                                  lstm_dim=512, observe_embeddings={'obs0': {'dim': 32}, 'obs1': {'dim': 32}})
+    n = 65536
+    eng = InferenceEngine.IMPORTANCE_SAMPLING_WITH_INFERENCE_NETWORK
+    for _ in range(2):
+        m.posterior_results(n, eng, observe={'obs0': 8, 'obs1': 9})
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        post = m.posterior_results(n, eng, observe={'obs0': 8, 'obs1': 9})
+        _ = post.effective_sample_size
+    torch.cuda.synchronize()
+    out['ic_posterior_gum_particles_per_sec_n65536'] = reps * n / (time.perf_counter() - t0)
     out.update(ic_posterior_extra())
     out.update(synthetic50_extra(dev))
     return out

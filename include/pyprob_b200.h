@@ -304,6 +304,10 @@ int ppb_ic_infer_step(ppb_net* net, const float* arena, const float* obs_emb /*[
 int ppb_ic_embed_observe(ppb_net* net, const float* arena, const float* obs, float* obs_emb_out,
                          int64_t n, void* workspace, int64_t workspace_bytes, void* stream);
 int64_t ppb_ic_infer_workspace_bytes(const ppb_net* net, int64_t n);
+/* Rebuild the packed tf32 tile images of all GEMM weights from the arena (done automatically by
+ * ppb_ic_loss_forward and ppb_ic_embed_observe; call it if the arena was modified by other means before
+ * ppb_ic_infer_step). */
+int ppb_net_refresh_weights(ppb_net* net, const float* arena, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 5. Host-buffer convenience entry (the end-to-end call bench.py times as `e2e`)

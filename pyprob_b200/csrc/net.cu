@@ -1289,6 +1289,8 @@ __global__ void __launch_bounds__(128) k_head_params(const float* __restrict__ o
 }
 
 struct InferWs {
+  HImg h_img, hid_img;        // tensor-core operands (K-format)
+  tcg::Problem* tprobs;
   float *gates, *hid, *out_raw, *smp_emb, *p_row, *emb_row, *w_smp_t;
   float* obs_act[PPB_MAX_OBS][PPB_MAX_FF_LAYERS];
   float* obs_cat;
@@ -1318,6 +1320,17 @@ InferWs carve_infer(const ppb_net* net, int64_t n, void* base) {
   for (int l = 0; l + 1 < D.obs_final.num_layers; ++l) w.fin_act[l] = take(n * D.obs_final.layers[l].out_dim);
   w.max_problems = 64 + 2LL * PPB_MAX_OBS * PPB_MAX_FF_LAYERS;
   w.problems = (Problem*)take(w.max_problems * (int64_t)(sizeof(Problem) / 4));
+  auto img_k = [&](int64_t rows, int64_t cols) {
+    HImg im;
+    int64_t nfl = img_floats(rows, cols);
+    off = align_up(off, 1024);
+    im.kb = (cols + 31) / 32;
+    im.k_hi = take(nfl); im.k_lo = take(nfl);
+    return im;
+  };
+  w.h_img = img_k(n, D.lstm_dim);
+  w.hid_img = img_k(n, net->dh_pad);
+  w.tprobs = (tcg::Problem*)take(8 * (int64_t)(sizeof(tcg::Problem) / 4));
   w.total_bytes = off;
   return w;
 }
@@ -1431,6 +1444,13 @@ int ppb_adam_step_dev(float* arena, const float* grad, float* exp_avg, float* ex
   return PPB_OK;
 }
 
+int ppb_net_refresh_weights(ppb_net* net, const float* arena, void* stream) {
+  PPB_CHECK_ARG(net && arena && net->wimg, "bad arguments (tables not set?)");
+  k_pack_table<<<dim3(net->pack_tiles, 8), 256, 0, (cudaStream_t)stream>>>(arena, net->d_pack, (int)net->pack.size(), net->wimg);
+  PPB_LAUNCH_CHECK();
+  return PPB_OK;
+}
+
 int64_t ppb_ic_infer_workspace_bytes(const ppb_net* net, int64_t n) {
   if (!net || n <= 0) return -1;
   return carve_infer(net, n, nullptr).total_bytes + 1024;
@@ -1442,6 +1462,10 @@ int ppb_ic_embed_observe(ppb_net* net, const float* arena, const float* obs, flo
   PPB_CHECK_ARG(workspace_bytes >= ppb_ic_infer_workspace_bytes(net, n), "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   InferWs w = carve_infer(net, n, workspace);
+  if (net->wimg) {  // inference starts here (_infer_init): bring the tensor-core weight images up to date
+    int rcw = ppb_net_refresh_weights(net, arena, stream);
+    if (rcw) return rcw;
+  }
   Builder bl;
   add_obs_embed(bl, net->desc, arena, obs, (int)n, w.obs_act, w.obs_cat, w.fin_act, obs_emb_out);
   int rc = upload_and_get(net, bl, w.problems, w.max_problems, st, 5);
@@ -1486,6 +1510,41 @@ int ppb_ic_infer_step(ppb_net* net, const float* arena, const float* obs_emb, in
                     (int)n, cur.head_out, cur.head_hidden, 0));
   int rc = upload_and_get(net, bl, w.problems, w.max_problems, st, 5);
   if (rc) return rc;
+  // large GEMMs on the tensor cores (weight images must be current: ppb_net_refresh_weights / ppb_ic_embed_observe)
+  const bool use_tc = precision != PPB_PREC_FP32_SIMT && (H % 32 == 0) && net->wimg != nullptr;
+  TcBuilder tb;
+  if (use_tc) {
+    tb.begin();  // 0: recurrent
+    if (!first) {
+      tcg::Problem p = TP0();
+      p.a = op_k(w.h_img.k_hi, w.h_img.k_lo, (int)w.h_img.kb, 0, 0);
+      p.b = wk(net, net->w_hh);
+      p.M = (int)n; p.N = H4; p.K = H; p.c = w.gates; p.ldc = H4;
+      tb.add(p);
+    }
+    tb.begin();  // 1: head trunk -> hid image
+    {
+      tcg::Problem p = TP0();
+      p.a = op_k(w.h_img.k_hi, w.h_img.k_lo, (int)w.h_img.kb, 0, 0);
+      p.b = wk(net, net->w1[cur_addr]);
+      p.M = (int)n; p.N = cur.head_hidden; p.K = H;
+      p.flags = tcg::kRelu; p.bias = arena + cur.b1_off;
+      p.o_k_hi = w.hid_img.k_hi; p.o_k_lo = w.hid_img.k_lo; p.o_kb = (int)w.hid_img.kb;
+      tb.add(p);
+    }
+    tb.begin();  // 2: head output
+    {
+      tcg::Problem p = TP0();
+      p.a = op_k(w.hid_img.k_hi, w.hid_img.k_lo, (int)w.hid_img.kb, 0, 0);
+      p.b = wk(net, net->w2[cur_addr]);
+      p.M = (int)n; p.N = cur.head_out; p.K = cur.head_hidden;
+      p.bias = arena + cur.b2_off; p.c = w.out_raw; p.ldc = net->out_pad;
+      tb.add(p);
+    }
+    rc = upload_cached(net, 6, tb.probs.data(), tb.probs.size() * sizeof(tcg::Problem), w.tprobs, st);
+    if (rc) return rc;
+  }
+  const dim3 pack_grid((unsigned)((n + 127) / 128), 4);
   k_step_row_infer<<<1, 128, 0, st>>>(arena, prev, first ? 0 : 1, cur, net->d_type_off, D.type_dim, D.addr_dim, w.emb_row);
   PPB_LAUNCH_CHECK();
   rc = run_phase(bl.phases[0], w.problems, st); if (rc) return rc;
@@ -1495,12 +1554,25 @@ int ppb_ic_infer_step(ppb_net* net, const float* arena, const float* obs_emb, in
     PPB_LAUNCH_CHECK();
     k_smp_embed_infer<<<ew_grid(n * S), 256, 0, st>>>(arena, prev, prev_value, n, S, w.smp_emb);
     PPB_LAUNCH_CHECK();
-    rc = run_phase(bl.phases[2], w.problems, st); if (rc) return rc;
+    if (use_tc) {
+      k_pack_rows<<<pack_grid, 256, 0, st>>>(h, (int)n, H, H, w.h_img);
+      PPB_LAUNCH_CHECK();
+      rc = run_tc_phase(tb.phases[0], w.tprobs, precision, st, 0); if (rc) return rc;
+    } else {
+      rc = run_phase(bl.phases[2], w.problems, st); if (rc) return rc;
+    }
   }
   k_cell_infer<<<ew_grid(n * H), 256, 0, st>>>(w.gates, w.p_row, w.w_smp_t, w.smp_emb, c, h, n, H, S, first ? 1 : 0);
   PPB_LAUNCH_CHECK();
-  rc = run_phase(bl.phases[3], w.problems, st); if (rc) return rc;
-  rc = run_phase(bl.phases[4], w.problems, st); if (rc) return rc;
+  if (use_tc) {
+    k_pack_rows<<<pack_grid, 256, 0, st>>>(h, (int)n, H, H, w.h_img);
+    PPB_LAUNCH_CHECK();
+    rc = run_tc_phase(tb.phases[1], w.tprobs, precision, st, 2); if (rc) return rc;
+    rc = run_tc_phase(tb.phases[2], w.tprobs, precision, st, 0); if (rc) return rc;
+  } else {
+    rc = run_phase(bl.phases[3], w.problems, st); if (rc) return rc;
+    rc = run_phase(bl.phases[4], w.problems, st); if (rc) return rc;
+  }
   k_head_params<<<ew_grid(n, 128), 128, 0, st>>>(w.out_raw, net->out_pad, cur, D.mixture_k, prior0, prior0_stride, prior1,
                                                  prior1_stride, params_out, n);
   PPB_LAUNCH_CHECK();

@@ -144,3 +144,72 @@ def test_loss_is_additive_over_sub_batches_and_grad_scales(cuda):
         loss2.backward()  # stale: other batches went through the shared workspace since
     # (a few reductions use atomics: summation order varies run to run)
     torch.testing.assert_close(net._arena.grad, g1 * 3.0, rtol=1e-4, atol=3e-5 * float(g1.abs().max()))
+
+
+def test_infer_step_tensor_core_vs_simt_and_oracle(cuda):
+    """Batched proposal step (ppb_ic_infer_step): the tensor-core path, the fp32 SIMT path and the oracle's
+    layer-by-layer restatement of _infer_step (inference_network_lstm.py:82-134) give the same proposal parameters."""
+    fx = netfixture.load('mixed')
+    n = 300
+    gen = torch.Generator().manual_seed(3)
+    obs = {name: torch.randn(d, generator=gen) for name, d in zip(fx['observe_names'], fx['observe_in_dims'])}
+    sb = fx['subs'][0]
+    seq = list(zip(sb['addresses'], sb['families'], sb['num_categories']))
+    vals = []
+    for a, fam, C in seq:
+        if fam == 'Categorical':
+            vals.append(torch.randint(0, C, (n,), generator=gen).float())
+        elif fam == 'Poisson':
+            vals.append(torch.poisson(torch.full((n,), 3.0), generator=gen))
+        else:
+            vals.append(torch.rand(n, generator=gen) * 1.5 - 0.5)
+    outs = {}
+    for precision in (0, 2):
+        net = _net_from_fixture(fx, precision)
+        net._infer_init(obs)
+        prev_a, prev_v, res = None, None, []
+        for (a, fam, C), v in zip(seq, vals):
+            p0 = {'Normal': 0.3, 'Uniform': -1.0}.get(fam)
+            p1 = {'Normal': 0.5, 'Uniform': 2.0}.get(fam)
+            params = net._infer_step_batched(a, prev_a, prev_v, p0, p1, n)
+            res.append(params.cpu())
+            prev_a, prev_v = a, v.to(cuda)
+        outs[precision] = res
+    for a, b in zip(outs[0], outs[2]):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
+    # oracle: step the reference-equivalent network for one particle path (all particles share the observation)
+    P = fx['params']
+    obs_row = torch.cat([obs[nm].reshape(-1) for nm in fx['observe_names']]).view(1, -1)
+    obs_emb = onet.embed_observe(P, obs_row, fx['observe_names'], fx['observe_in_dims']).expand(n, -1)
+    H, K = fx['lstm_dim'], fx['K']
+    h = torch.zeros(n, H)
+    c = torch.zeros(n, H)
+    for t, ((a, fam, C), v) in enumerate(zip(seq, vals)):
+        cur_t, cur_a = P['_layers_distribution_type_embedding.' + fam], P['_layers_address_embedding.' + a]
+        if t == 0:
+            smp, pt, pa = torch.zeros(n, 4), torch.zeros(8), torch.zeros(64)
+        else:
+            pa_, pf, pc = seq[t - 1]
+            smp = onet.sample_embedding(P, pa_, pf, pc, vals[t - 1])
+            pt, pa = P['_layers_distribution_type_embedding.' + pf], P['_layers_address_embedding.' + pa_]
+        x = torch.cat([obs_emb, smp, torch.cat([pt, pa, cur_t, cur_a]).expand(n, -1)], dim=1)
+        g = x @ P['_layers_lstm.weight_ih_l0'].t() + P['_layers_lstm.bias_ih_l0'] + h @ P['_layers_lstm.weight_hh_l0'].t() \
+            + P['_layers_lstm.bias_hh_l0']
+        i, f, gg, o = torch.sigmoid(g[:, :H]), torch.sigmoid(g[:, H:2 * H]), torch.tanh(g[:, 2 * H:3 * H]), torch.sigmoid(g[:, 3 * H:])
+        c = f * c + i * gg
+        h = o * torch.tanh(c)
+        raw = onet._ff(h, P, '_layers_proposal.{}._ff'.format(a), False)
+        got = outs[0][t]
+        if fam == 'Categorical':
+            want = torch.softmax(raw, dim=1) + 1e-8
+        else:
+            coeffs = torch.softmax(raw[:, 2 * K:], dim=1)
+            if fam == 'Normal':
+                means, sds = 0.3 + raw[:, :K] * 0.5, torch.exp(raw[:, K:2 * K]) * 0.5
+            elif fam == 'Uniform':
+                means = -1.0 + torch.sigmoid(raw[:, :K]) * 3.0
+                sds = 3.0 / 1000 + torch.sigmoid(raw[:, K:2 * K]) * 3.0 * 10
+            else:
+                means, sds = torch.sigmoid(raw[:, :K]) * 40.0, torch.exp(raw[:, K:2 * K])
+            want = torch.cat([means, sds, coeffs], dim=1)
+        torch.testing.assert_close(got, want, rtol=2e-4, atol=1e-5)
