@@ -1414,6 +1414,8 @@ int ppb_batch_from_image(const void* image_host, const void* image_dev, int64_t 
     out->row_next = (const int32_t*)(Dv + hd[25]);
     out->step_t = (const int32_t*)(Dv + hd[26]);
     out->step_prev_row0 = (const int32_t*)(Dv + hd[27]);
+    out->group_addr = (const int32_t*)(Dv + hd[10]);
+    out->group_start = (const int32_t*)(Dv + hd[11]);
   }
   return PPB_OK;
 }

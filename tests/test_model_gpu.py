@@ -125,7 +125,7 @@ def test_marsaglia_inference_compilation(cuda):
     pyprob.seed(5)
     pyprob.set_verbosity(0)
     model = GaussianUnknownMeanMarsaglia()
-    model.learn_inference_network(num_traces=120000, batch_size=256, inference_network=InferenceNetwork.LSTM,
+    model.learn_inference_network(num_traces=300000, batch_size=512, inference_network=InferenceNetwork.LSTM,
                                   lstm_dim=128, observe_embeddings={'obs0': {'dim': 16}, 'obs1': {'dim': 16}})
     post = model.posterior_results(8192, InferenceEngine.IMPORTANCE_SAMPLING_WITH_INFERENCE_NETWORK,
                                    observe={'obs0': 8, 'obs1': 9})
