@@ -164,6 +164,8 @@ def main():
     ap.add_argument('--precision', type=int, default=0)
     ap.add_argument('--no-extra', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--nccl-allreduce', action='store_true',
+                    help='N>1: NCCL all-reduce + local Adam instead of the fused peer-memory optimiser step')
     args = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -201,7 +203,18 @@ def main():
     if world > 1:
         dist.broadcast(net._arena.data, 0)
     nparams = net._arena.numel()
-    grad = torch.zeros(nparams, device=dev)
+    peer = None
+    if world > 1 and not args.nccl_allreduce:
+        # data-parallel step = ONE kernel over NVLink peer memory: reduce-scatter + Adam on the owned slice +
+        # all-gather of the parameters (ppb_dp_adam_step); the arena and the gradient live in the peer block
+        from pyprob_b200 import parallel
+        peer = parallel.PeerAdam(nparams, dev)
+        peer.params.copy_(net._arena.data)
+        net._arena_store = peer.params
+        net._arena = torch.nn.Parameter(peer.params)
+        grad = peer.grad[:nparams]
+    else:
+        grad = torch.zeros(nparams, device=dev)
     net._arena.grad = grad
     batches = [synthetic.gum_batch(rng, BATCH) for _ in range(4)]
     encs = [b.encode(net) for b in batches]
@@ -218,7 +231,8 @@ def main():
     from pyprob_b200.network import BatchStruct
     hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 0.0, 1.0 / world], dtype=torch.float32, device=dev)
     adam_state = torch.zeros(4, dtype=torch.int32, device=dev)
-    loss = torch.empty((), device=dev)
+    # the loss rides in the gradient tail so that the fused collective sums it with the gradient
+    loss = peer.grad[nparams:nparams + 1].view(()) if peer is not None else torch.empty((), device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     # all batches of the workload share one structure: one "current batch" image in HBM is refreshed (device to
     # device) from the resident batches, so the index/problem lists are built and uploaded once
@@ -236,6 +250,9 @@ def main():
              args.precision, ptr(loss), ptr(status), None, 1, torch.cuda.current_stream().cuda_stream)
         call('ppb_ic_loss_backward', net._handle, ptr(net._arena.data), ptr(grad), C.byref(bs), ptr(net._workspace), need,
              args.precision, 1.0, torch.cuda.current_stream().cuda_stream)
+        if peer is not None:
+            peer.step(net._exp_avg, net._exp_avg_sq, hyper, adam_state, torch.cuda.current_stream().cuda_stream)
+            return
         if world > 1:
             dist.all_reduce(grad)
         call('ppb_adam_step_dev', ptr(net._arena.data), ptr(grad), ptr(net._exp_avg), ptr(net._exp_avg_sq), nparams,
@@ -324,6 +341,8 @@ def main():
     e2e_ms = float(t.item())
     e2e_value = args.steps * BATCH * world / (e2e_ms * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
+    if peer is not None and peer.timed_out():
+        raise RuntimeError('fused data-parallel step: a cross-rank barrier timed out; the measurement is void')
 
     # ---- roofline of the gate-GEMM class: per-launch durations from CUDA events inside the step ---------------
     peaks = measured_peaks()
@@ -363,6 +382,8 @@ def main():
                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                'config': {'workload': WORKLOAD, 'global_batch': BATCH * world, 'lstm_dim': LSTM_DIM, 'trace_length': 1,
                           'parameters': nparams, 'parallelism': 'dp{}'.format(world),
+                          'collective': None if world == 1 else ('fused reduce-scatter+Adam+all-gather over NVLink '
+                                                                 'peer memory' if peer is not None else 'nccl all-reduce'),
                           'precision': ['3xTF32', 'TF32', 'fp32-simt'][args.precision],
                           'l2': 'flushed between timed steps (256 MiB memset outside the timed spans)',
                           'cuda_graph': bool(use_graph)},

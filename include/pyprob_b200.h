@@ -293,6 +293,31 @@ int ppb_adam_step(float* arena, const float* grad, float* exp_avg, float* exp_av
 int ppb_adam_step_dev(float* arena, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                       const float* hyper_dev, void* state_dev, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Data-parallel optimiser step fused with its collective (replaces the per-parameter gradient
+ * all-reduce + optimizer.step() of pyprob/nn/inference_network.py:296-333, :496).
+ *
+ * Every rank owns one "peer block" of device memory that all ranks of the node map over NVLink
+ * (CUDA IPC).  Block layout (byte offsets chosen by the caller, 16-byte aligned, identical on all ranks):
+ *   param_off : float[n]            parameter arena (replicated)
+ *   grad_off  : float[n + n_extra]  this rank's gradient, then n_extra piggy-backed scalars (loss ...)
+ *   flag_off  : uint32[64]          barrier words, zero before the first step
+ * ppb_dp_adam_step is ONE kernel: cross-rank barrier -> each rank sums ITS 1/world slice of the gradient
+ * over all peers in fixed rank order (reduce-scatter by peer loads) -> Adam on that slice (exp_avg /
+ * exp_avg_sq are local, only the slice is touched) -> the updated parameters are stored into every peer's
+ * arena (all-gather by peer stores) -> cross-rank barrier.  The n_extra scalars are summed by rank 0 and
+ * written back to every rank's gradient tail.  Replicas stay bit-identical: every element is reduced by
+ * exactly one rank.  hyper_dev/state_dev as for ppb_adam_step_dev (grad_scale = 1/world). The call is
+ * CUDA-graph capturable; all ranks must issue it the same number of times. */
+int ppb_dp_alloc(int64_t bytes, void** ptr_out, void* ipc_handle_out /* 64 bytes */);
+int ppb_dp_open(const void* ipc_handle /* 64 bytes, from another process */, void** ptr_out);
+int ppb_dp_close(void* mapped_ptr);
+int ppb_dp_free(void* ptr);
+int ppb_dp_adam_step(int world, int rank, void* const* peer_blocks /* host array [world], own block at [rank] */,
+                     int64_t param_off, int64_t grad_off, int64_t flag_off, float* exp_avg,
+                     float* exp_avg_sq, int64_t n, int64_t n_extra, const float* hyper_dev, void* state_dev,
+                     void* stream);
+
 /* Batched proposal step for IC posterior sampling (inference_network_lstm.py:82-134 for n particles in
  * lock-step at the same address).  h/c: fp32[n,H] LSTM state, updated in place (zeros at t=0).
  * prev_addr < 0 means first step.  Writes the proposal parameters:

@@ -56,6 +56,11 @@ _SIGNATURES = {
     'ppb_ic_loss_backward': [C.c_void_p, c_f, c_f, C.c_void_p, c_f, c_i64, c_int, c_flt, c_f],
     'ppb_adam_step': [c_f, c_f, c_f, c_f, c_i64, c_flt, c_flt, c_flt, c_flt, c_flt, c_i64, c_flt, c_f],
     'ppb_adam_step_dev': [c_f, c_f, c_f, c_f, c_i64, c_f, c_f, c_f],
+    'ppb_dp_alloc': [c_i64, C.c_void_p, C.c_void_p],
+    'ppb_dp_open': [C.c_void_p, C.c_void_p],
+    'ppb_dp_close': [c_f],
+    'ppb_dp_free': [c_f],
+    'ppb_dp_adam_step': [c_int, c_int, C.c_void_p, c_i64, c_i64, c_i64, c_f, c_f, c_i64, c_i64, c_f, c_f, c_f],
     'ppb_ic_infer_step': [C.c_void_p, c_f, c_f, c_int, c_i32, c_f, c_i32, c_f, c_int, c_f, c_int, c_f, c_f, c_f,
                           c_i64, c_f, c_i64, c_int, c_f],
     'ppb_ic_embed_observe': [C.c_void_p, c_f, c_f, c_f, c_i64, c_f, c_i64, c_f],

@@ -49,6 +49,18 @@ static inline int ppb_grid_for(int64_t n, int threads, int items_per_thread, int
   return (int)blocks;
 }
 
+// One Adam update (torch.optim.Adam without amsgrad) with every rounding spelled out, so that the plain, the
+// device-state and the data-parallel fused optimiser kernels produce the same bits:
+//   g' = g*gscale + wd*p;  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;  p -= step * m / (sqrt(v)/bc2_sqrt + eps)
+__device__ __forceinline__ void ppb_adam_update(float& p, float g, float& m, float& v, float b1, float b2, float eps,
+                                                float wd, float gscale, float step, float bc2_sqrt) {
+  float gr = __fmaf_rn(g, gscale, __fmul_rn(wd, p));
+  m = __fmaf_rn(b1, m, __fmul_rn(1.0f - b1, gr));
+  v = __fmaf_rn(b2, v, __fmul_rn(__fmul_rn(1.0f - b2, gr), gr));
+  float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2_sqrt), eps);
+  p = __fsub_rn(p, __fdiv_rn(__fmul_rn(step, m), denom));
+}
+
 // ---- math constants (fp32, written the way torch.distributions writes them) -------------------
 #define PPB_LOG_SQRT_2PI 0.9189385332046727f  // math.log(math.sqrt(2*math.pi))
 #define PPB_INV_SQRT2 0.7071067811865476f

@@ -1155,23 +1155,16 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
     float pa[4] = {pp.x, pp.y, pp.z, pp.w}, ga[4] = {gg.x, gg.y, gg.z, gg.w};
     float ma[4] = {mm.x, mm.y, mm.z, mm.w}, va[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float gr = ga[j] * gscale + wd * pa[j];
-      ma[j] = b1 * ma[j] + (1.0f - b1) * gr;
-      va[j] = b2 * va[j] + (1.0f - b2) * gr * gr;
-      pa[j] -= step * ma[j] / (sqrtf(va[j]) / bc2_sqrt + eps);
-    }
+    for (int j = 0; j < 4; ++j) ppb_adam_update(pa[j], ga[j], ma[j], va[j], b1, b2, eps, wd, gscale, step, bc2_sqrt);
     reinterpret_cast<float4*>(p)[q] = make_float4(pa[0], pa[1], pa[2], pa[3]);
     reinterpret_cast<float4*>(m)[q] = make_float4(ma[0], ma[1], ma[2], ma[3]);
     reinterpret_cast<float4*>(v)[q] = make_float4(va[0], va[1], va[2], va[3]);
   }
   for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
-    float gr = g[i] * gscale + wd * p[i];
-    float mi = b1 * m[i] + (1.0f - b1) * gr;
-    float vi = b2 * v[i] + (1.0f - b2) * gr * gr;
-    m[i] = mi; v[i] = vi;
-    p[i] -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    float pi = p[i], mi = m[i], vi = v[i];
+    ppb_adam_update(pi, g[i], mi, vi, b1, b2, eps, wd, gscale, step, bc2_sqrt);
+    m[i] = mi; v[i] = vi; p[i] = pi;
   }
 }
 
@@ -1189,11 +1182,9 @@ __global__ void __launch_bounds__(256) k_adam_dev(float* __restrict__ p, const f
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], gscale = hyper[5];
   const float step = lr / bc[0], bc2_sqrt = bc[1];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float gr = g[i] * gscale + wd * p[i];
-    float mi = b1 * m[i] + (1.0f - b1) * gr;
-    float vi = b2 * v[i] + (1.0f - b2) * gr * gr;
-    m[i] = mi; v[i] = vi;
-    p[i] -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    float pi = p[i], mi = m[i], vi = v[i];
+    ppb_adam_update(pi, g[i], mi, vi, b1, b2, eps, wd, gscale, step, bc2_sqrt);
+    m[i] = mi; v[i] = vi; p[i] = pi;
   }
 }
 

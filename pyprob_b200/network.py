@@ -125,6 +125,7 @@ class InferenceNetworkLSTM(nn.Module):
         self._optimizer_step = 0
         self._exp_avg = None
         self._exp_avg_sq = None
+        self._peer = None                 # parallel.PeerAdam when training data-parallel over NVLink
         self._learning_rate_init = None
         self._learning_rate_end = None
         self._learning_rate_scheduler_type = None
@@ -387,8 +388,11 @@ class InferenceNetworkLSTM(nn.Module):
     def __getstate__(self):
         st = self.__dict__.copy()
         for k in ('_handle', '_workspace', '_image_dev', '_image_host', '_loss_buf', '_model',
-                  '_infer_observe_embedding'):
+                  '_infer_observe_embedding', '_peer', '_peer_hyper', '_peer_state'):
             st[k] = None
+        if self._peer is not None:   # the arena lives in an NVLink peer block: pickle a private copy
+            st['_arena_store'] = self._arena_store.clone()
+            st['_arena'] = nn.Parameter(st['_arena_store'][:self._arena_used])
         st['_tables_dirty'] = True
         return st
 
@@ -507,6 +511,33 @@ class InferenceNetworkLSTM(nn.Module):
              self._arena.numel(), float(self._learning_rate), b1, b2, self._adam_eps, float(self._weight_decay or 0.0),
              self._optimizer_step, float(grad_scale), stream())
 
+    def _enable_peer_optimizer(self):
+        """Move the arena into this rank's NVLink peer block and switch the optimiser step to the fused
+        reduce-scatter + Adam + all-gather kernel (parallel.PeerAdam).  Arena offsets are unchanged."""
+        n = self._arena.numel()
+        peer = parallel.PeerAdam(n, self._arena.device)
+        peer.params.copy_(self._arena.data)
+        self._arena_store = peer.params
+        self._arena = nn.Parameter(peer.params)
+        self._peer = peer
+        self._peer_hyper = torch.zeros(6, dtype=torch.float32, device=peer.params.device)
+        self._peer_state = torch.zeros(4, dtype=torch.int32, device=peer.params.device)
+        self._peer_state.view(torch.int64)[0] = int(self._optimizer_step)
+
+    def _peer_optimizer_step(self, loss, world):
+        peer, n = self._peer, self._arena.numel()
+        peer.grad[:n].copy_(self._arena.grad)
+        peer.grad[n:n + 1].copy_(loss.reshape(1))
+        b1, b2 = self._adam_betas
+        self._peer_hyper.copy_(torch.tensor([float(self._learning_rate), b1, b2, self._adam_eps,
+                                             float(self._weight_decay or 0.0), 1.0 / world]))
+        peer.step(self._exp_avg, self._exp_avg_sq, self._peer_hyper, self._peer_state, stream())
+        self._optimizer_step += 1
+        loss_value = float(peer.grad[n]) / world
+        if peer.timed_out():
+            raise RuntimeError('pyprob_b200: data-parallel optimiser step timed out waiting for a peer rank')
+        return loss_value
+
     # ------------------------------------------------------------------------------------------------
     # training loop (reference: inference_network.py:381-599)
     # ------------------------------------------------------------------------------------------------
@@ -559,6 +590,8 @@ class InferenceNetworkLSTM(nn.Module):
                                    '_pre_generate_layers first so that every rank holds the same arena layout')
             if self._exp_avg is None or layers_changed:
                 self._create_optimizer()
+            if world > 1 and self._peer is None and distributed_backend == 'nccl':
+                self._enable_peer_optimizer()
             if world > 1 and self._total_train_iterations == 0:
                 dist.broadcast(self._arena.data, 0)
             self._arena.grad = None
@@ -569,10 +602,14 @@ class InferenceNetworkLSTM(nn.Module):
                     return
                 continue
             loss.backward()
-            # one all-reduce over the flat gradient arena, loss scalar piggy-backed
-            loss_value, grad_scale = parallel.allreduce_grad_and_loss(self._arena.grad, loss.detach())
             self._learning_rate = self._current_learning_rate()
-            self.optimizer_step(grad_scale)
+            if self._peer is not None:
+                # reduce-scatter + Adam + all-gather in one kernel over NVLink peer memory
+                loss_value = self._peer_optimizer_step(loss.detach(), world)
+            else:
+                # one all-reduce over the flat gradient arena, loss scalar piggy-backed
+                loss_value, grad_scale = parallel.allreduce_grad_and_loss(self._arena.grad, loss.detach())
+                self.optimizer_step(grad_scale)
             if self._loss_init is None:
                 self._loss_init = loss_value
                 self._loss_max = loss_value
