@@ -46,28 +46,72 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.  The region lasts tens of milliseconds, far
+    below nvidia-smi's loop period, so NVML is polled directly every ~2 ms from a thread; `nvidia-smi -lms` is
+    the fallback when the NVML binding is missing."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
+    NVML_REASONS = ((0x8, 'hw_slowdown'), (0x40, 'hw_thermal_slowdown'), (0x20, 'sw_thermal_slowdown'),
+                    (0x4, 'sw_power_cap'), (0x80, 'hw_power_brake_slowdown'))
 
-    def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    def __init__(self, gpu_index, uuid=None):
+        self.rows, self.proc, self.gpu, self.uuid = [], None, gpu_index, uuid
+        self.nvml, self.handle, self.thread, self.halt = None, None, None, False
+        self.sm, self.mask, self.sm_max = [], 0, None
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            handle = None
+            if self.uuid is not None:
+                try:
+                    handle = pynvml.nvmlDeviceGetHandleByUUID('GPU-' + str(self.uuid))
+                except Exception:
+                    handle = None
+            if handle is None:
+                visible = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+                ids = [x for x in visible.split(',') if x.strip().isdigit()]
+                phys = int(ids[self.gpu]) if self.gpu < len(ids) else self.gpu
+                handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            self.reasons_fn = getattr(pynvml, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.nvml, self.handle = pynvml, handle
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                          '--format=csv,noheader,nounits', '-lms', '20'], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        while not self.halt:
+            try:
+                self.sm.append(float(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)))
+                self.mask |= int(self.reasons_fn(self.handle))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(',')])
 
     def stop(self):
+        if self.nvml is not None:
+            self.halt = True
+            self.thread.join(1.0)
+            reasons = sorted(nm for bit, nm in self.NVML_REASONS if self.mask & bit)
+            return {'sm_mhz': float(np.median(self.sm)) if self.sm else None, 'sm_max_mhz': self.sm_max,
+                    'reasons': reasons, 'samples': len(self.sm), 'source': 'nvml, 2 ms period'}
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.proc.terminate()
@@ -81,7 +125,7 @@ class ClockSampler:
                     if r[5 + k].lower().startswith('active'):
                         reasons.add(nm)
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm), 'source': 'nvidia-smi -lms 20'}
 
 
 # ---- CPU arm: the oracle port of the reference path -------------------------------------------------------
@@ -282,7 +326,7 @@ def main():
             graphs[i % 4].replay()
         else:
             device_step(i)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, getattr(torch.cuda.get_device_properties(dev), 'uuid', None))
     if rank == 0:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]

@@ -112,7 +112,7 @@ def gum_is_fixture(seed=7, n=64):
             'gum_ess': np.asarray(float(post.effective_sample_size))}
 
 
-if __name__ == '__main__':
+def make_scoring_fixtures():
     fx = scoring_fixture()
     fx.update(gum_is_fixture())
     np.savez_compressed(os.path.join(HERE, 'scoring_golden.npz'), **fx)
@@ -221,4 +221,5 @@ def make_network_fixtures():
 
 
 if __name__ == '__main__':
+    make_scoring_fixtures()
     make_network_fixtures()
