@@ -1,6 +1,7 @@
 """Data-parallel plumbing (torch.distributed): the ONE collective of the training step and the particle
-sharding helpers.  Pure torch, device-agnostic — the same code runs over NCCL on the GPUs and over gloo in
-the CPU tests (tests/test_parallel_gloo.py).
+sharding helpers.  The all-reduce helpers are pure torch and device-agnostic — the same code runs over NCCL on
+the GPUs and over gloo in the CPU tests (tests/test_parallel_gloo.py).  On one NVLink node the training step uses
+``PeerAdam`` instead: the gradient exchange and the optimiser fused into one kernel over peer memory.
 
 Reference semantics (pyprob/nn/inference_network.py:296-333, :448, :529-530): every rank draws its own
 minibatch, gradients are summed over ranks and divided by the world size, the loss is averaged, the learning
