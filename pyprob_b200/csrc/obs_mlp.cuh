@@ -7,7 +7,7 @@
 
 namespace obsmlp {
 
-constexpr int TB = 16;       // traces per CTA
+constexpr int TB = 4;        // traces per CTA: the chain is latency-bound, so favour CTAs in flight (64 at B=256)
 constexpr int WMAX = 256;    // widest activation handled on chip
 constexpr int LD = WMAX + 1;
 constexpr int NC = 64;       // output columns per staged weight chunk
