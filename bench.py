@@ -420,9 +420,18 @@ def main():
     if rank == 0 and world == 1:
         cpu_baseline, _ = cpu_reference_arm(10 ** 6, 2, budget_s=args.cpu_budget)
         if not args.no_extra:
-            extra = posterior_extras(dev)
-            extra['scoring_hbm_roofline'] = scoring_rooflines(dev, peaks)
-            extra['gate_gemm_saturating_4096x2048x512'] = gate_gemm_saturating(dev, peaks)
+            # secondary workloads: a failure here must not cost the headline line
+            for key, fn in (('posterior', lambda: posterior_extras(dev)),
+                            ('scoring_hbm_roofline', lambda: scoring_rooflines(dev, peaks)),
+                            ('gate_gemm_saturating_4096x2048x512', lambda: gate_gemm_saturating(dev, peaks))):
+                try:
+                    res = fn()
+                    if key == 'posterior':
+                        extra.update(res)
+                    else:
+                        extra[key] = res
+                except Exception as exc:   # noqa: BLE001 - reported in the JSON line
+                    extra[key + '_error'] = '{}: {}'.format(type(exc).__name__, exc)
             extra['hbm_peak_gbs'] = peaks['hbm_gbs']
     if rank == 0:
         out = {'metric': 'ic_train_traces_per_sec', 'value': value, 'unit': 'traces/s', 'n_gpus': world,
