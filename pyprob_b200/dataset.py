@@ -85,6 +85,38 @@ class TraceBatch:
         self._encoded = EncodedBatch(subs, row_align=net.row_align)
         return self._encoded
 
+    def to_sub_batches(self, observe_names):
+        """Host copy of the minibatch as plain arrays, one dict per sub-batch (the form synthetic.ArrayBatch and
+        offline.TraceColumns.from_sub_batches take): addresses/families/num_categories per step, values, prior0,
+        prior1 [T, B] and obs [B, sum of observable sizes]."""
+        n = self.trace.n
+        obs = torch.cat([self.trace.named_variables[name].value.reshape(n, -1).float() for name in observe_names],
+                        dim=1).cpu().numpy()
+
+        def host(x):
+            return (x.reshape(n).float().cpu().numpy() if torch.is_tensor(x) else np.full(n, float(x), np.float32))
+        zeros = np.zeros(n, np.float32)
+        subs = []
+        for sites, idx in self.groups:
+            sel = slice(None) if idx is None else idx.cpu().numpy()
+            addresses, families, cats, vals, p0, p1 = [], [], [], [], [], []
+            for s in sites:
+                d = s.distribution
+                addresses.append(s.address)
+                families.append(d.name)
+                cats.append(d.num_categories if isinstance(d, Categorical) else 0)
+                vals.append(host(s.value)[sel])
+                if isinstance(d, Normal):
+                    p0.append(host(d.loc)[sel]); p1.append(host(d.scale)[sel])
+                elif isinstance(d, Uniform):
+                    p0.append(host(d.low)[sel]); p1.append(host(d.high)[sel])
+                else:
+                    p0.append(zeros[sel]); p1.append(zeros[sel])
+            subs.append({'addresses': addresses, 'families': families, 'num_categories': cats,
+                         'values': np.stack(vals, 0), 'prior0': np.stack(p0, 0), 'prior1': np.stack(p1, 0),
+                         'obs': obs[sel]})
+        return subs
+
 
 class OnlineDataset:
     def __init__(self, model, length=None, prior_inflation=PriorInflation.DISABLED):
@@ -106,3 +138,25 @@ class OnlineDataset:
             self._example = self._model._run_batched(1, trace_mode=TraceMode.PRIOR_FOR_INFERENCE_NETWORK,
                                                      prior_inflation=self._prior_inflation)
         return self._example
+
+    def save_dataset(self, dataset_dir, num_traces, num_traces_per_file, observe_names, batch_size=None):
+        """Generate prior traces on the GPU and write them as columnar trace files (reference:
+        OnlineDataset.save_dataset, pyprob/nn/dataset.py:121-137 — one file per num_traces_per_file traces)."""
+        from . import offline
+        names = []
+        written = 0
+        while written < num_traces:
+            count = num_traces_per_file   # like the reference, every file is full: ceil(num_traces / per file) files
+            chunks, have = [], 0
+            while have < count:
+                b = min(batch_size or count, count - have)
+                batch = self.next_batch(b)
+                subs = batch.to_sub_batches(observe_names)
+                dims = [int(np.prod(batch.trace.value_shape(batch.trace.named_variables[nm])))
+                        for nm in observe_names]
+                chunks.append(offline.TraceColumns.from_sub_batches(subs, observe_names, dims))
+                have += b
+            cols = chunks[0] if len(chunks) == 1 else offline.concat_columns(chunks)
+            names.append(offline.save_columns(dataset_dir, cols))
+            written += count
+        return names

@@ -12,6 +12,7 @@ from .dataset import OnlineDataset
 from .distributions import set_shard_first_index
 from .empirical import Empirical
 from .network import InferenceNetworkLSTM
+from .offline import OfflineDataset
 from .util import InferenceEngine, InferenceNetwork, LearningRateScheduler, Optimizer, PriorInflation, TraceMode
 
 
@@ -160,22 +161,33 @@ class Model:
                                 distributed_backend=None, distributed_params_sync_every_iter=10000,
                                 distributed_num_buckets=None, dataloader_offline_num_workers=0, stop_with_bad_loss=True,
                                 log_file_name=None, lstm_dim=512, lstm_depth=1, proposal_mixture_components=10):
-        if dataset_dir is not None or dataset_valid_dir is not None:
-            raise NotImplementedError('offline datasets are out of scope for pyprob_b200 (SURVEY.md 8f)')
         if inference_network != InferenceNetwork.LSTM:
             raise NotImplementedError('pyprob_b200 implements InferenceNetwork.LSTM (the path north_star names)')
-        dataset = OnlineDataset(model=self, prior_inflation=prior_inflation)
+        names = list(observe_embeddings.keys())
+        if dataset_dir is None:
+            dataset = OnlineDataset(model=self, prior_inflation=prior_inflation)
+        else:
+            dataset = OfflineDataset(dataset_dir, verbose=True)
+            dataset.select_observables(names if names else dataset.observe_names)
+        dataset_valid = None
+        if dataset_valid_dir is not None:
+            dataset_valid = OfflineDataset(dataset_valid_dir, verbose=True)
+            dataset_valid.select_observables(names if names else dataset_valid.observe_names)
         if self._inference_network is None:
             print('Creating new inference network...')
             self._inference_network = InferenceNetworkLSTM(model=self, observe_embeddings=observe_embeddings,
                                                            lstm_dim=lstm_dim, lstm_depth=lstm_depth,
                                                            proposal_mixture_components=proposal_mixture_components)
             if pre_generate_layers:
-                self._inference_network._pre_generate_layers(dataset, batch_size=batch_size)
+                if dataset_valid is not None:
+                    self._inference_network._pre_generate_layers(dataset_valid, batch_size=batch_size,
+                                                                 save_file_name_prefix=save_file_name_prefix)
+                self._inference_network._pre_generate_layers(dataset, batch_size=batch_size,
+                                                             save_file_name_prefix=save_file_name_prefix)
         else:
             print('Continuing to train existing inference network...')
         self._inference_network.optimize(
-            num_traces=num_traces, dataset=dataset, dataset_valid=None, num_traces_end=num_traces_end,
+            num_traces=num_traces, dataset=dataset, dataset_valid=dataset_valid, num_traces_end=num_traces_end,
             batch_size=batch_size, valid_every=valid_every, optimizer_type=optimizer_type,
             learning_rate_init=learning_rate_init, learning_rate_end=learning_rate_end,
             learning_rate_scheduler_type=learning_rate_scheduler_type, momentum=momentum, weight_decay=weight_decay,
@@ -185,6 +197,15 @@ class Model:
             distributed_num_buckets=distributed_num_buckets,
             dataloader_offline_num_workers=dataloader_offline_num_workers, stop_with_bad_loss=stop_with_bad_loss,
             log_file_name=log_file_name)
+
+    def save_dataset(self, dataset_dir, num_traces, num_traces_per_file, prior_inflation=PriorInflation.DISABLED,
+                     observe_names=None, batch_size=None):
+        """Write prior traces as columnar trace files (reference Model.save_dataset, model.py:226-231).  All named
+        variables of the model are stored as observables unless ``observe_names`` restricts them."""
+        dataset = OnlineDataset(model=self, prior_inflation=prior_inflation)
+        if observe_names is None:
+            observe_names = [name for name in dataset.example_trace().named_variables]
+        return dataset.save_dataset(dataset_dir, num_traces, num_traces_per_file, observe_names, batch_size=batch_size)
 
     def save_inference_network(self, file_name):
         if self._inference_network is None:

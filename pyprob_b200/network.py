@@ -575,6 +575,18 @@ class InferenceNetworkLSTM(nn.Module):
             self._total_train_traces_end = num_traces_end
         trace, stop = 0, False
         last_save = time_start
+        if hasattr(dataset, 'num_buckets'):      # offline data: bucketed rank-strided sampling (dataset.py:330-400)
+            dataset.num_buckets = distributed_num_buckets
+        if dataset_valid is not None:
+            if hasattr(dataset_valid, 'num_buckets'):
+                dataset_valid.num_buckets = distributed_num_buckets
+            if not self._layers_pre_generated:   # reference inference_network.py:412-414
+                for vbatch in dataset_valid.epoch_batches(batch_size):
+                    self._polymorph(vbatch)
+        if valid_every is None:
+            valid_every = max(100, num_traces / 1000)
+        last_validation_trace = -valid_every + 1
+        valid_loss = 0
         log_file = None
         if rank == 0 and log_file_name is not None:
             log_file = open(log_file_name, mode='w', buffering=1)
@@ -624,6 +636,11 @@ class InferenceNetworkLSTM(nn.Module):
             self._history_train_loss_trace.append(self._total_train_traces)
             traces_per_second = batch.size * world / max(time_batch - time_last_batch, 1e-9)
             time_last_batch = time_batch
+            if dataset_valid is not None and trace - last_validation_trace > valid_every:
+                valid_loss = self._validation_loss(dataset_valid, batch_size, world)
+                self._history_valid_loss.append(valid_loss)
+                self._history_valid_loss_trace.append(self._total_train_traces)
+                last_validation_trace = trace - 1
             if rank == 0 and save_file_name_prefix is not None and save_every_sec is not None:
                 if time_batch - last_save > save_every_sec:
                     last_save = time_batch
@@ -637,19 +654,48 @@ class InferenceNetworkLSTM(nn.Module):
                     self._loss_init, self._loss_min, self._learning_rate, traces_per_second))
             if log_file is not None:
                 log_file.write('{}, {}, {}, {}, {}, {}, {}, {}, {}, {}\n'.format(
-                    self._total_train_seconds, self._total_train_iterations, self._total_train_traces, loss_value, 0,
-                    self._learning_rate, batch.mean_length_controlled, batch.num_sub_batches, None, traces_per_second))
+                    self._total_train_seconds, self._total_train_iterations, self._total_train_traces, loss_value,
+                    valid_loss, self._learning_rate, batch.mean_length_controlled, batch.num_sub_batches,
+                    getattr(dataset, 'current_bucket_id', None), traces_per_second))
         if log_file is not None:
             log_file.close()
         if rank == 0 and save_file_name_prefix is not None:
             self._save('{}_{}_traces_{}.network'.format(save_file_name_prefix, util.get_time_stamp(),
                                                        self._total_train_traces))
 
+    def _validation_loss(self, dataset_valid, batch_size, world):
+        """Mean minibatch loss over one pass of the validation set (reference inference_network.py:534-546): the
+        sum of the per-minibatch losses of this rank's share, divided by (minibatches / world), averaged over
+        ranks."""
+        total, count = 0.0, 0
+        with torch.no_grad():
+            for vbatch in dataset_valid.epoch_batches(batch_size):
+                success, v = self._loss(vbatch)
+                if success:
+                    total += float(v)
+                count += 1
+        denom = dataset_valid.num_batches(batch_size) / world if world > 1 else count
+        value = total / max(denom, 1e-9)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([value], dtype=torch.float32, device=self._arena.device)
+            dist.all_reduce(t)
+            value = float(t) / world
+        return value
+
     def _pre_generate_layers(self, dataset, batch_size=64, save_file_name_prefix=None, num_batches=16):
         self._ensure_initialized(dataset.example_trace())
         self._layers_pre_generated = True
-        for _ in range(num_batches):
-            self._polymorph(dataset.next_batch(batch_size))
+        if hasattr(dataset, 'address_signature'):
+            # offline data: the files carry their address table, so one call sees what a full pass of the reference's
+            # batch-by-batch _polymorph would discover (inference_network.py:270-288), in the same order
+            changed = self._polymorph(dataset)
+        else:
+            changed = False
+            for _ in range(num_batches):
+                changed = self._polymorph(dataset.next_batch(batch_size)) or changed
+        if changed and save_file_name_prefix is not None:
+            self._save('{}_00000000_pre_generated.network'.format(save_file_name_prefix))
 
     # ------------------------------------------------------------------------------------------------
     # checkpoint (reference: inference_network.py:162-263)
