@@ -76,3 +76,72 @@ def test_single_trace_and_single_step_edge_cases():
     enc = EncodedBatch([one])
     assert (enc.n_traces, enc.n_rows, enc.n_steps, enc.n_groups, enc.t_max) == (1, 1, 1, 1, 1)
     assert enc.arrays['row_prev'][0] == -1 and enc.arrays['step_prev_addr'][0] == -1
+
+
+def _random_subs(seed):
+    rng = np.random.default_rng(seed)
+    subs = []
+    for _ in range(int(rng.integers(1, 6))):
+        T, B = int(rng.integers(1, 9)), int(rng.integers(1, 300))
+        subs.append(SubBatch(rng.integers(0, 7, T), rng.normal(size=(T, B)), rng.normal(size=(T, B)),
+                             rng.uniform(0.5, 2, size=(T, B)), rng.normal(size=(B, 3))))
+    return subs
+
+
+def test_row_align_128_pads_every_segment_to_whole_tiles_and_keeps_the_payload():
+    for seed in range(8):
+        subs = _random_subs(seed)
+        compact, tiled = EncodedBatch(subs, row_align=1), EncodedBatch(subs, row_align=128)
+        a, c = tiled.arrays, compact.arrays
+        assert tiled.row_align == 128 and tiled.n_traces == compact.n_traces and tiled.n_steps == compact.n_steps
+        assert np.all(a['step_row0'] % 128 == 0) and np.all(a['row_off'] % 128 == 0) and tiled.n_rows % 128 == 0
+        np.testing.assert_array_equal(a['step_addr'], c['step_addr'])
+        np.testing.assert_array_equal(a['step_nrows'], c['step_nrows'])
+        np.testing.assert_array_equal(a['step_t'], c['step_t'])
+        valid = a['row_trace'] >= 0
+        assert int(valid.sum()) == compact.n_rows == tiled.n_valid_rows
+        # padding rows: no trace, no neighbours, neutral payload, but they still belong to their segment's step
+        pad = ~valid
+        assert np.all(a['row_prev'][pad] == -1) and np.all(a['row_next'][pad] == -1)
+        assert np.all(a['values'][pad] == 0) and np.all(a['prior0'][pad] == 0) and np.all(a['prior1'][pad] == 1)
+        assert np.all(a['row_step'] >= 0)
+        for st in range(tiled.n_steps):
+            r0, nb = a['step_row0'][st], a['step_nrows'][st]
+            seg = (nb + 127) // 128 * 128
+            assert np.all(a['row_step'][r0:r0 + seg] == st)
+            assert np.all(a['row_trace'][r0:r0 + nb] >= 0) and np.all(a['row_trace'][r0 + nb:r0 + seg] == -1)
+        # same (trace, time) -> same payload in both layouts
+        key_t = {(int(tr), int(a['step_t'][a['row_step'][r]])): r for r, tr in enumerate(a['row_trace']) if tr >= 0}
+        for r in range(compact.n_rows):
+            k = (int(c['row_trace'][r]), int(c['step_t'][c['row_step'][r]]))
+            rt = key_t[k]
+            assert a['values'][rt] == c['values'][r] and a['prior0'][rt] == c['prior0'][r]
+            assert a['prior1'][rt] == c['prior1'][r]
+        # row_next is the inverse of row_prev on valid rows; chains walk t = 0..T-1 of one trace
+        has_prev = np.nonzero(a['row_prev'] >= 0)[0]
+        np.testing.assert_array_equal(a['row_next'][a['row_prev'][has_prev]], has_prev)
+        np.testing.assert_array_equal(a['row_trace'][a['row_prev'][has_prev]], a['row_trace'][has_prev])
+        # the head row lists only name valid rows, each exactly once
+        assert sorted(a['head_rows'].tolist()) == np.nonzero(valid)[0].tolist()
+
+
+def test_structure_key_ignores_payload_and_sees_shape():
+    subs = _random_subs(3)
+    other = [SubBatch(s.addr_ids, s.values + 1, s.prior0, s.prior1, s.obs) for s in subs]
+    assert EncodedBatch(subs, 128).structure_key() == EncodedBatch(other, 128).structure_key()
+    assert EncodedBatch(subs, 128).structure_key() != EncodedBatch(subs, 1).structure_key()
+    fewer = [SubBatch(s.addr_ids, s.values[:, :1], s.prior0[:, :1], s.prior1[:, :1], s.obs[:1]) for s in subs]
+    assert EncodedBatch(subs, 128).structure_key() != EncodedBatch(fewer, 128).structure_key()
+
+
+def test_errors_empty_batch_and_short_image_buffer():
+    import pytest
+    with pytest.raises(ValueError):
+        EncodedBatch([])
+    enc = EncodedBatch(_random_subs(1), 128)
+    with pytest.raises(ValueError):
+        enc.pack(out=np.zeros(64, np.uint8))
+    buf = np.zeros(enc.offsets()[1] + 100, np.uint8)
+    img = enc.pack(out=buf)
+    assert img.nbytes == enc.offsets()[1] and img[:8].view(np.int64)[0] == IMAGE_MAGIC
+    assert img[28 * 8:29 * 8].view(np.int64)[0] == 128
