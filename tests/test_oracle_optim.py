@@ -1,0 +1,44 @@
+"""CPU: the flat-arena optimiser restatement (oracle/optim.py) against trajectories produced by torch.optim wrapped
+in the reference's own LARC class (tests/golden/optim_golden.npz), including tensors whose gradient is absent on
+some steps."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import optim as ooptim
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _load():
+    return dict(np.load(os.path.join(HERE, 'golden', 'optim_golden.npz')))
+
+
+@pytest.mark.parametrize('tag', ['adam_wd0.0', 'adam_wd0.01', 'adam_larc_wd0.001', 'sgd_larc_wd0.001', 'sgd_wd0.01'])
+def test_flat_optimiser_matches_torch_and_reference_larc(tag):
+    z = _load()
+    sizes = [int(x) for x in z['shapes']]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    segs = [(int(offs[k]), sizes[k]) for k in range(len(sizes))]
+    lr, wd = float(z[tag + '/lr']), float(z[tag + '/wd'])
+    p = torch.from_numpy(z[tag + '/init'].copy())
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    steps = torch.zeros(len(segs), dtype=torch.int64)
+    seen = torch.zeros(len(segs), dtype=torch.bool)
+    for step in range(int(z['steps'])):
+        g = torch.from_numpy(z['{}/grad{}'.format(tag, step)].copy())
+        present = [bool(x) for x in z['{}/present{}'.format(tag, step)]]
+        eff_wd = wd
+        if tag.split('_wd')[0].endswith('larc'):
+            ooptim.larc_adjust(p, g, present, segs, lr, wd)
+            eff_wd = 0.0
+        if tag.startswith('adam'):
+            ooptim.adam_step(p, g, m, v, steps, present, segs, lr, weight_decay=eff_wd)
+        else:
+            ooptim.sgd_step(p, g, m, seen, present, segs, lr, momentum=0.9, weight_decay=eff_wd)
+        want = z['{}/param{}'.format(tag, step)]
+        np.testing.assert_allclose(p.numpy(), want, rtol=2e-6, atol=2e-7, err_msg='{} step {}'.format(tag, step))
+    # a tensor that was absent keeps its value and its step count
+    assert int(steps[2]) in (0, int(z['steps']) - 2)
