@@ -293,6 +293,26 @@ int ppb_adam_step(float* arena, const float* grad, float* exp_avg, float* exp_av
 int ppb_adam_step_dev(float* arena, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                       const float* hyper_dev, void* state_dev, void* stream);
 
+/* Segment-aware optimiser step (pyprob/nn/inference_network.py:343-355, pyprob/nn/optimizer_larc.py:74-107):
+ * Adam or Nesterov SGD (dampening 0), optionally under LARC (clip mode), over a flat arena whose parameter
+ * tensors ("segments") may be absent from the minibatch.  An absent segment is skipped exactly as torch skips a
+ * parameter whose .grad is None: no moment decay, no step-count increment, no LARC scaling.
+ *   kind            0 Adam, 1 Adam+LARC, 2 SGD, 3 SGD+LARC
+ *   n               arena length in floats; segments start on multiples of 4 (16-byte aligned regions)
+ *   seg_of_block    int32[ceil(n/4)] device: segment id of floats [4i, 4i+4), -1 for padding
+ *   present         int32[n_segs] device: 1 if the segment received a gradient this step
+ *   seg_steps       int64[n_segs] device: per-segment step counts (incremented for present segments)
+ *   state0/state1   Adam: exp_avg / exp_avg_sq;  SGD: momentum buffer / unused (may be NULL)
+ *   hyper_dev       float[10] device: lr, beta1, beta2, eps, weight_decay, grad_scale, momentum,
+ *                   larc trust coefficient (0.002), larc eps (1e-8), larc epsilon (1/16000)
+ *   scratch         ppb_optimizer_scratch_bytes(n_segs) bytes of device memory
+ * Graph-capturable (all step-dependent state lives in device memory). */
+int64_t ppb_optimizer_scratch_bytes(int32_t n_segs);
+int ppb_optimizer_step_segmented(float* arena, const float* grad, float* state0, float* state1, int64_t n,
+                                 const int32_t* seg_of_block_dev, int32_t n_segs, const int32_t* present_dev,
+                                 int64_t* seg_steps_dev, void* scratch_dev, int64_t scratch_bytes, int kind,
+                                 const float* hyper_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Data-parallel optimiser step fused with its collective (replaces the per-parameter gradient
  * all-reduce + optimizer.step() of pyprob/nn/inference_network.py:296-333, :496).

@@ -56,6 +56,8 @@ _SIGNATURES = {
     'ppb_ic_loss_backward': [C.c_void_p, c_f, c_f, C.c_void_p, c_f, c_i64, c_int, c_flt, c_f],
     'ppb_adam_step': [c_f, c_f, c_f, c_f, c_i64, c_flt, c_flt, c_flt, c_flt, c_flt, c_i64, c_flt, c_f],
     'ppb_adam_step_dev': [c_f, c_f, c_f, c_f, c_i64, c_f, c_f, c_f],
+    'ppb_optimizer_scratch_bytes': [c_i32],
+    'ppb_optimizer_step_segmented': [c_f, c_f, c_f, c_f, c_i64, c_f, c_i32, c_f, c_f, c_f, c_i64, c_int, c_f, c_f],
     'ppb_dp_alloc': [c_i64, C.c_void_p, C.c_void_p],
     'ppb_dp_open': [C.c_void_p, C.c_void_p],
     'ppb_dp_close': [c_f],
@@ -81,9 +83,10 @@ _RESTYPES = {
     'ppb_packed_floats': c_i64,
     'ppb_sizeof': c_i64,
     'ppb_launch_count': c_i64,
+    'ppb_optimizer_scratch_bytes': c_i64,
 }
 # entry points whose integer return value is data, not a status
-_VALUE_RETURNS = {'ppb_version', 'ppb_device_arch', 'ppb_weights_num_partials', 'ppb_ic_workspace_bytes',
+_VALUE_RETURNS = {'ppb_optimizer_scratch_bytes', 'ppb_version', 'ppb_device_arch', 'ppb_weights_num_partials', 'ppb_ic_workspace_bytes',
                   'ppb_ic_infer_workspace_bytes', 'ppb_packed_floats', 'ppb_sizeof', 'ppb_launch_count'}
 
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES.keys()) + ['ppb_last_error'])

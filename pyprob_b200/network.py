@@ -13,6 +13,7 @@ Same constructor keywords, attributes and method names as the reference
 """
 import ctypes as C
 import math
+import os
 import time
 import warnings
 from collections import OrderedDict
@@ -26,6 +27,8 @@ from ._lib import call, ptr, stream
 from .encoding import EncodedBatch
 from .util import InferenceNetwork as InferenceNetworkType  # noqa: F401
 from .util import LearningRateScheduler, ObserveEmbedding, Optimizer
+
+_OPTIMIZER_KIND = {Optimizer.ADAM: 0, Optimizer.ADAM_LARC: 1, Optimizer.SGD: 2, Optimizer.SGD_LARC: 3}
 
 FAMILY_NORMAL, FAMILY_UNIFORM, FAMILY_POISSON, FAMILY_CATEGORICAL = 0, 1, 2, 3
 _FAMILY_OF = {'Normal': FAMILY_NORMAL, 'Uniform': FAMILY_UNIFORM, 'Poisson': FAMILY_POISSON,
@@ -126,6 +129,9 @@ class InferenceNetworkLSTM(nn.Module):
         self._exp_avg = None
         self._exp_avg_sq = None
         self._peer = None                 # parallel.PeerAdam when training data-parallel over NVLink
+        self._seg = None                  # device tables of the segment-aware optimiser step (LARC / SGD / skipping)
+        self._skip_absent_gradients = False   # True: tensors absent from a minibatch are skipped like .grad None
+        self._last_enc = None
         self._learning_rate_init = None
         self._learning_rate_end = None
         self._learning_rate_scheduler_type = None
@@ -388,7 +394,7 @@ class InferenceNetworkLSTM(nn.Module):
     def __getstate__(self):
         st = self.__dict__.copy()
         for k in ('_handle', '_workspace', '_image_dev', '_image_host', '_loss_buf', '_model',
-                  '_infer_observe_embedding', '_peer', '_peer_hyper', '_peer_state'):
+                  '_infer_observe_embedding', '_peer', '_peer_hyper', '_peer_state', '_seg', '_last_enc'):
             st[k] = None
         if self._peer is not None:   # the arena lives in an NVLink peer block: pickle a private copy
             st['_arena_store'] = self._arena_store.clone()
@@ -454,6 +460,7 @@ class InferenceNetworkLSTM(nn.Module):
         enc = batch.encode(self)
         if enc is None:
             return False, 0
+        self._last_enc = enc
         for address, _, _ in batch.address_signature():
             self._head_iterations[address] += 1
         if torch.is_grad_enabled():
@@ -479,17 +486,93 @@ class InferenceNetworkLSTM(nn.Module):
     def _create_optimizer(self, state=None):
         if self._optimizer_type is None:
             return
-        if self._optimizer_type not in (Optimizer.ADAM,):
-            raise NotImplementedError('pyprob_b200: only Optimizer.ADAM is implemented on the fused path')
+        if self._optimizer_type not in _OPTIMIZER_KIND:
+            raise NotImplementedError('pyprob_b200: unknown optimizer type {}'.format(self._optimizer_type))
         n = self._arena.numel()
         self._exp_avg = torch.zeros(n, dtype=torch.float32, device='cuda')
         self._exp_avg_sq = torch.zeros(n, dtype=torch.float32, device='cuda')
         self._optimizer_step = 0
         self._learning_rate = self._learning_rate_init
+        self._seg = None
+        if self._optimizer_type != Optimizer.ADAM or self._skip_absent_gradients:
+            self._create_segment_state()
         if state is not None:
             self._exp_avg.copy_(state['exp_avg'])
             self._exp_avg_sq.copy_(state['exp_avg_sq'])
             self._optimizer_step = state['step']
+            if self._seg is not None and state.get('segment_steps') is not None:
+                self._seg['steps'].copy_(state['segment_steps'])
+
+    def _create_segment_state(self):
+        """Device tables of the segment-aware optimiser step (ppb_optimizer_step_segmented): one segment per parameter
+        tensor of the reference.  Needed for LARC / SGD (per-tensor norms, per-tensor first-step flag) and for the
+        reference's skipping of tensors whose gradient is absent from a minibatch (`_skip_absent_gradients`)."""
+        if os.environ.get('PPB_RUN_UNVALIDATED') != '1':
+            raise NotImplementedError(
+                'pyprob_b200: Optimizer.{} runs on the segment-aware optimiser kernels (csrc/optim.cu), which have not '
+                'been validated on hardware yet; set PPB_RUN_UNVALIDATED=1 to use them, or train with Optimizer.ADAM'
+                .format(self._optimizer_type.name))
+        names = sorted(self.parameter_index, key=lambda k: self.parameter_index[k][0])
+        n = self._arena.numel()
+        seg_of_block = np.full((n + 3) // 4, -1, dtype=np.int32)
+        for k, name in enumerate(names):
+            off, shape = self.parameter_index[name]
+            seg_of_block[off // 4:(off + int(np.prod(shape)) + 3) // 4] = k
+        S = len(names)
+        scratch = _lib.call('ppb_optimizer_scratch_bytes', S)
+        self._seg = {'names': names, 'index': {nm: k for k, nm in enumerate(names)},
+                     'seg_of_block': torch.from_numpy(seg_of_block).cuda(),
+                     'steps': torch.zeros(S, dtype=torch.int64, device='cuda'),
+                     'present': torch.ones(S, dtype=torch.int32, device='cuda'),
+                     'scratch': torch.empty(int(scratch), dtype=torch.uint8, device='cuda'),
+                     'hyper': torch.zeros(10, dtype=torch.float32, device='cuda')}
+
+    def _segment_presence(self, enc):
+        """int32[S]: 1 for every parameter tensor that took part in the forward pass of the encoded minibatch, i.e.
+        whose .grad the reference's autograd would populate (all others stay None and are skipped by torch.optim):
+        shared layers always; address / type embeddings and the proposal head of every address in the batch; the
+        sample-embedding layer of every address that is some step's PREVIOUS address (inference_network_lstm.py:
+        150-182)."""
+        seg = self._seg
+        present = np.ones(len(seg['names']), dtype=np.int32)
+        if not self._skip_absent_gradients or enc is None:
+            return present
+        by_id = {info['id']: (a, info) for a, info in self._addresses.items()}
+        cur = set(int(i) for i in np.unique(enc.arrays['step_addr']))
+        prev = set(int(i) for i in np.unique(enc.arrays['step_prev_addr']) if i >= 0)
+        types = set(by_id[i][1]['type'] for i in cur | prev)
+        for k, name in enumerate(seg['names']):
+            if name.startswith('_layers_address_embedding.'):
+                a = name[len('_layers_address_embedding.'):]
+                present[k] = int(self._addresses[a]['id'] in cur)
+            elif name.startswith('_layers_distribution_type_embedding.'):
+                present[k] = int(name[len('_layers_distribution_type_embedding.'):] in types)
+            elif name.startswith('_layers_proposal.'):
+                a = name[len('_layers_proposal.'):name.index('._ff._layers.')]
+                present[k] = int(self._addresses[a]['id'] in cur)
+            elif name.startswith('_layers_sample_embedding.'):
+                a = name[len('_layers_sample_embedding.'):name.index('._layers.')]
+                present[k] = int(self._addresses[a]['id'] in prev)
+        return present
+
+    def _segmented_optimizer_step(self, grad_scale):
+        seg = self._seg
+        b1, b2 = self._adam_betas
+        seg['present'].copy_(torch.from_numpy(self._segment_presence(self._last_enc)))
+        world, _ = parallel.world_info()
+        if world > 1 and self._skip_absent_gradients:
+            # a tensor is present if any rank saw it (the reference's presence map, inference_network.py:299-311)
+            import torch.distributed as dist
+            dist.all_reduce(seg['present'], op=dist.ReduceOp.MAX)
+        seg['hyper'].copy_(torch.tensor([float(self._learning_rate), b1, b2, self._adam_eps,
+                                         float(self._weight_decay or 0.0), float(grad_scale),
+                                         float(self._momentum if self._momentum is not None else 0.9),
+                                         0.002, 1e-8, 1.0 / 16000.0]))
+        adam = self._optimizer_type in (Optimizer.ADAM, Optimizer.ADAM_LARC)
+        call('ppb_optimizer_step_segmented', ptr(self._arena.data), ptr(self._arena.grad), ptr(self._exp_avg),
+             ptr(self._exp_avg_sq) if adam else None, self._arena.numel(), ptr(seg['seg_of_block']), len(seg['names']),
+             ptr(seg['present']), ptr(seg['steps']), ptr(seg['scratch']), seg['scratch'].numel(),
+             _OPTIMIZER_KIND[self._optimizer_type], ptr(seg['hyper']), stream())
 
     @property
     def _optimizer(self):
@@ -506,6 +589,9 @@ class InferenceNetworkLSTM(nn.Module):
 
     def optimizer_step(self, grad_scale=1.0):
         self._optimizer_step += 1
+        if self._seg is not None:
+            self._segmented_optimizer_step(grad_scale)
+            return
         b1, b2 = self._adam_betas
         call('ppb_adam_step', ptr(self._arena.data), ptr(self._arena.grad), ptr(self._exp_avg), ptr(self._exp_avg_sq),
              self._arena.numel(), float(self._learning_rate), b1, b2, self._adam_eps, float(self._weight_decay or 0.0),
@@ -602,7 +688,7 @@ class InferenceNetworkLSTM(nn.Module):
                                    '_pre_generate_layers first so that every rank holds the same arena layout')
             if self._exp_avg is None or layers_changed:
                 self._create_optimizer()
-            if world > 1 and self._peer is None and distributed_backend == 'nccl':
+            if world > 1 and self._peer is None and self._seg is None and distributed_backend == 'nccl':
                 self._enable_peer_optimizer()
             if world > 1 and self._total_train_iterations == 0:
                 dist.broadcast(self._arena.data, 0)
@@ -705,7 +791,8 @@ class InferenceNetworkLSTM(nn.Module):
         self._updates += 1
         data = {'pyprob_b200_version': 1, 'torch_version': torch.__version__, 'inference_network': self,
                 'optimizer_state': None if self._exp_avg is None else
-                {'exp_avg': self._exp_avg.cpu(), 'exp_avg_sq': self._exp_avg_sq.cpu(), 'step': self._optimizer_step}}
+                {'exp_avg': self._exp_avg.cpu(), 'exp_avg_sq': self._exp_avg_sq.cpu(), 'step': self._optimizer_step,
+                 'segment_steps': None if self._seg is None else self._seg['steps'].cpu()}}
         torch.save(data, file_name)
 
     @staticmethod
@@ -716,6 +803,8 @@ class InferenceNetworkLSTM(nn.Module):
         ret._arena = nn.Parameter(ret._arena_store[:ret._arena_used])
         ret._handle = None
         ret._tables_dirty = True
+        for k, default in (('_peer', None), ('_seg', None), ('_skip_absent_gradients', False), ('_last_enc', None)):
+            ret.__dict__.setdefault(k, default)   # checkpoints written before these attributes existed
         if data['optimizer_state'] is not None:
             ret._create_optimizer(data['optimizer_state'])
         return ret

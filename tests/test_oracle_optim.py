@@ -42,3 +42,39 @@ def test_flat_optimiser_matches_torch_and_reference_larc(tag):
         np.testing.assert_allclose(p.numpy(), want, rtol=2e-6, atol=2e-7, err_msg='{} step {}'.format(tag, step))
     # a tensor that was absent keeps its value and its step count
     assert int(steps[2]) in (0, int(z['steps']) - 2)
+
+
+def test_segment_presence_matches_autograd_none_pattern():
+    """Host logic of the segment-aware optimiser: which parameter tensors count as present for a minibatch must be
+    exactly the tensors torch autograd populates in the reference's graph (all others keep .grad None and are skipped
+    by torch.optim).  Ground truth: autograd through the oracle's restatement of _loss on reference-named parameters."""
+    from oracle import network as onet
+    from pyprob_b200.encoding import EncodedBatch, SubBatch
+    from pyprob_b200.network import InferenceNetworkLSTM
+    from tests import netfixture
+    fx = netfixture.load('mixed')
+    fam_of = {}
+    for sb in fx['subs']:
+        for a, f in zip(sb['addresses'], sb['families']):
+            fam_of[a] = f
+    net = InferenceNetworkLSTM(model=None, observe_embeddings={n: {} for n in fx['observe_names']})
+    net._addresses = {a: {'id': i, 'type': fam_of[a]} for i, a in enumerate(fx['address_order'])}
+    names = sorted(fx['params'])
+    net._seg = {'names': names}
+    net._skip_absent_gradients = True
+    ids = {a: i for i, a in enumerate(fx['address_order'])}
+    checked_absent = 0
+    for chosen in ([0], [1], list(range(len(fx['subs'])))):
+        subs = [fx['subs'][i] for i in chosen]
+        p = {k: v.clone().float().requires_grad_(True) for k, v in fx['params'].items()}
+        value, _ = onet.loss(p, subs, fx['observe_names'], fx['observe_in_dims'], fx['K'])
+        value.backward()
+        want = np.asarray([int(p[n].grad is not None) for n in names])
+        enc = EncodedBatch([SubBatch([ids[a] for a in sb['addresses']], sb['values'].numpy(), sb['prior0'].numpy(),
+                                     sb['prior1'].numpy(), sb['obs'].numpy()) for sb in subs])
+        got = net._segment_presence(enc)
+        assert got.tolist() == want.tolist(), [n for n, a, b in zip(names, got, want) if a != b]
+        checked_absent += int((want == 0).sum())
+    assert checked_absent > 0   # the single-sub-batch cases really leave some tensors without a gradient
+    net._skip_absent_gradients = False
+    assert net._segment_presence(enc).min() == 1
