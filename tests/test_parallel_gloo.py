@@ -80,3 +80,55 @@ def test_shard_range_partitions():
             assert spans[0][0] == 0 and sum(c for _, c in spans) == n
             for (f0, c0), (f1, _) in zip(spans, spans[1:]):
                 assert f0 + c0 == f1
+
+
+def _offline_worker(rank, world, port, path, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from pyprob_b200 import offline
+    ds = offline.OfflineDataset(path)
+    ds.num_buckets = 3
+    np.random.seed(50 + rank)
+    per_epoch = None
+    seen = []
+    for epoch in range(2):
+        batches = []
+        # one epoch of this rank's share: the sampler yields the same number of minibatches on every rank
+        sampler = ds._make_sampler(16)
+        if per_epoch is None:
+            per_epoch = sum(1 for _ in sampler)
+            ds._sampler_iter = None
+        for _ in range(per_epoch):
+            b = ds.next_batch(16)
+            batches.append((b.size, sorted(float(x) for sb in b.subs for x in sb['values'][0])))
+        seen.append(batches)
+    q.put((rank, per_epoch, seen))
+    dist.destroy_process_group()
+
+
+def test_offline_dataset_shards_minibatches_over_ranks_world2(tmp_path):
+    """The training loop's data side under torch.distributed: OfflineDataset.next_batch picks the bucketed,
+    rank-strided sampler (reference dataset.py:330-400); ranks see disjoint minibatches and run in lock step."""
+    from pyprob_b200 import offline, synthetic
+    rng = np.random.default_rng(0)
+    table = [('a_n', 'Normal', 0), ('a_u', 'Uniform', 0)]
+    subs = [synthetic.random_sub_batch(rng, [table[i] for i in seq], B, 2) for seq, B in (([0], 300), ([0, 1], 220))]
+    offline.save_columns(str(tmp_path), offline.TraceColumns.from_sub_batches(subs, ['o'], [2]))
+    world, port = 2, 29741
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_offline_worker, args=(r, world, port, str(tmp_path), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == res[1][1] > 0                      # same number of iterations per epoch on both ranks
+    for epoch in range(2):
+        a = [tuple(v) for _, v in res[0][2][epoch]]
+        b = [tuple(v) for _, v in res[1][2][epoch]]
+        assert all(size == 16 for size, _ in res[0][2][epoch] + res[1][2][epoch])
+        assert not set(a) & set(b)                         # disjoint minibatches
+        assert len(set(a)) == len(a) and len(set(b)) == len(b)
