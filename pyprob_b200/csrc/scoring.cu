@@ -2,6 +2,8 @@
 // Replaces pyprob/distributions/distribution.py:38-43 as driven per particle by pyprob/state.py.
 // Algorithmic bytes per element: Normal/Uniform 16 B, Poisson 12 B, Categorical 4C+12 B,
 // Mixture-Normal (3K+2)*4 B, Mixture-TruncatedNormal (3K+4)*4 B.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -192,12 +194,104 @@ __global__ void __launch_bounds__(kThreads) k_mixture(const float* __restrict__ 
   }
 }
 
+// Same arithmetic, parameters staged through shared memory: a CTA copies the contiguous [256, K] parameter rows
+// of its tile with coalesced 128-bit loads, then every thread reads its own row from shared memory (instead of 3K
+// strided 4-byte global loads per thread).  Requires densely packed rows (row_stride == K) and 16-byte aligned
+// arrays.  STATUS: opt-in (PPB_MIXTURE_STAGED=1) until its first hardware run — written after the round-1 GPU budget
+// was spent; results must be bit-identical to k_mixture.
+template <int KMAX, bool TRUNC>
+__global__ void __launch_bounds__(kThreads) k_mixture_staged(const float* __restrict__ value,
+                                                              const float* __restrict__ means,
+                                                              const float* __restrict__ stddevs,
+                                                              const float* __restrict__ probs, int K, Param low,
+                                                              Param high, Sink out, int64_t n) {
+  extern __shared__ __align__(16) float sm[];
+  float* sm_m = sm;
+  float* sm_s = sm + kThreads * K;
+  float* sm_p = sm + 2 * kThreads * K;
+  for (int64_t tile0 = (int64_t)blockIdx.x * kThreads; tile0 < n; tile0 += (int64_t)gridDim.x * kThreads) {
+    const int rows = (int)((n - tile0 < kThreads) ? (n - tile0) : kThreads);
+    const int cnt = rows * K;
+    const float* gm = means + tile0 * K;
+    const float* gs = stddevs + tile0 * K;
+    const float* gp = probs + tile0 * K;
+    for (int idx = threadIdx.x * 4; idx < cnt; idx += kThreads * 4) {
+      if (idx + 4 <= cnt) {
+        *reinterpret_cast<float4*>(sm_m + idx) = ldg_stream4(gm + idx);
+        *reinterpret_cast<float4*>(sm_s + idx) = ldg_stream4(gs + idx);
+        *reinterpret_cast<float4*>(sm_p + idx) = ldg_stream4(gp + idx);
+      } else {
+        for (int j = idx; j < cnt; ++j) {
+          sm_m[j] = __ldg(gm + j);
+          sm_s[j] = __ldg(gs + j);
+          sm_p[j] = __ldg(gp + j);
+        }
+      }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < rows) {
+      const int64_t i = tile0 + threadIdx.x;
+      const float* m = sm_m + threadIdx.x * K;
+      const float* sd = sm_s + threadIdx.x * K;
+      const float* p = sm_p + threadIdx.x * K;
+      float v = __ldg(value + i);
+      float lo = 0.f, hi = 0.f;
+      if (TRUNC) { lo = low.at(i); hi = high.at(i); }
+      float t[KMAX];
+      float psum = 0.0f;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k)
+        if (k < K) psum += p[k];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        if (k < K) {
+          float lw = logf(ppb_clamp_prob(p[k] / psum));
+          float lpk = TRUNC ? ppb_truncnormal_lp(v, m[k], sd[k], lo, hi) : ppb_normal_lp(v, m[k], sd[k]);
+          t[k] = lw + lpk;
+          mx = fmaxf(mx, t[k]);
+        }
+      }
+      float r;
+      if (mx == -INFINITY) {
+        r = -INFINITY;
+      } else {
+        float acc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+          if (k < K) acc += expf(t[k] - mx);
+        r = mx + logf(acc);
+      }
+      out.put(i, r);
+    }
+    __syncthreads();
+  }
+}
+
+inline bool mixture_staged_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("PPB_MIXTURE_STAGED");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+
 template <bool TRUNC>
 int launch_mixture(const float* value, const float* means, const float* stddevs, const float* probs,
                    int64_t row_stride, int K, Param low, Param high, Sink out, int64_t n, void* stream) {
   if (n == 0) return PPB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   int grid = ppb_grid_for(n, kThreads, 1);
+  if (mixture_staged_enabled() && row_stride == K && K <= 10 && aligned16(means) && aligned16(stddevs) &&
+      aligned16(probs)) {
+    size_t smem = (size_t)3 * kThreads * K * sizeof(float);
+    if (K <= 4)
+      k_mixture_staged<4, TRUNC><<<grid, kThreads, smem, st>>>(value, means, stddevs, probs, K, low, high, out, n);
+    else
+      k_mixture_staged<10, TRUNC><<<grid, kThreads, smem, st>>>(value, means, stddevs, probs, K, low, high, out, n);
+    PPB_LAUNCH_CHECK();
+    return PPB_OK;
+  }
   if (K <= 4)
     k_mixture<4, TRUNC><<<grid, kThreads, 0, st>>>(value, means, stddevs, probs, row_stride, K, low, high, out, n);
   else if (K <= 10)
