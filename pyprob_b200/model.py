@@ -163,7 +163,7 @@ class Model:
                                 log_file_name=None, lstm_dim=512, lstm_depth=1, proposal_mixture_components=10):
         if inference_network != InferenceNetwork.LSTM:
             raise NotImplementedError('pyprob_b200 implements InferenceNetwork.LSTM (the path north_star names)')
-        names = list(observe_embeddings.keys())
+        names = list(observe_embeddings)   # dict (or set) of observable names
         if dataset_dir is None:
             dataset = OnlineDataset(model=self, prior_inflation=prior_inflation)
         else:
