@@ -10,12 +10,14 @@
 // which removes the T-fold recomputation of the observation block.
 #include <vector>
 #include <string.h>
+#include <stdlib.h>
 #include <stdint.h>
 
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "heads.cuh"
 #include "tc_grouped.cuh"
+#include "tc_lstm.cuh"
 #include "obs_mlp.cuh"
 
 using gemm::Problem;
@@ -63,6 +65,12 @@ struct ppb_net {
   int I = 0;        // LSTM input width  E + S + 2 (td + ad)
   int dh_pad = 4;   // max head hidden width, padded to 4
   int out_pad = 4;  // max head output width, padded to 4
+  // opt-in (PPB_FUSED_CELL=1, unvalidated): LSTM cell fused into the recurrent GEMM epilogue (tc_lstm.cuh)
+  int fused_cell = 0;
+  float* whh_il = nullptr;          // gate-interleaved K-format image of W_hh: hi part, then lo part
+  int64_t whh_il_floats = 0;        // floats per part
+  void* d_lstm_steps = nullptr;     // device list of tcl::Step
+  size_t lstm_steps_cap = 0;        // bytes
   // pinned staging ring for problem lists
   Problem* h_stage[2] = {nullptr, nullptr};
   cudaEvent_t ev_stage[2] = {nullptr, nullptr};
@@ -805,6 +813,8 @@ int ppb_net_create(ppb_net** out, const ppb_net_desc* d) {
   ppb_net* n = new ppb_net();
   n->desc = *d;
   n->I = d->obs_dim + d->sample_dim + 2 * (d->type_dim + d->addr_dim);
+  const char* fc = getenv("PPB_FUSED_CELL");
+  n->fused_cell = (fc && fc[0] == '1') ? 1 : 0;
   *out = n;
   return PPB_OK;
 }
@@ -847,6 +857,8 @@ int ppb_net_destroy(ppb_net* net) {
   }
   if (net->wimg) cudaFree(net->wimg);
   if (net->d_pack) cudaFree(net->d_pack);
+  if (net->whh_il) cudaFree(net->whh_il);
+  if (net->d_lstm_steps) cudaFree(net->d_lstm_steps);
   delete net;
   return PPB_OK;
 }

@@ -1,0 +1,242 @@
+// LSTM time step with the cell update fused into the recurrent GEMM's epilogue.
+//
+//   pre[:, g*H + u] = h_{t-1} W_hh^T  (tcgen05, 3xTF32 or TF32)  + P_obs[trace] + P_step[segment] + smp_emb W_smp
+//   i,f,o = sigmoid, g = tanh;  c_t = f c_{t-1} + i g;  h_t = o tanh(c_t)          (torch.nn.LSTM, gate order i,f,g,o)
+//
+// replaces, for t >= 1, the pair (tcg::k_grouped<X3,0> writing fp32 gate pre-activations, k_cell_fwd re-reading
+// them): pyprob/nn/inference_network_lstm.py:186-188.  The trick is the weight layout: W_hh is packed with
+// GATE-INTERLEAVED rows — packed row ub*128 + g*32 + j  <-  original row g*H + ub*32 + j — so that the 128 output
+// columns of one tile are the four gates of the SAME 32 hidden units, and epilogue warp (q, cb) holds gate cb of rows
+// 32q..32q+31.  Each warp finishes its gate (adds the projections, applies the activation, stores it for the
+// backward pass, keeps it in its staging block); after a 128-thread named barrier per row quadrant the four warps
+// each complete 8 rows of the cell: c, h, and the K-/MN-format tile images of h that the next step, the heads and
+// the weight-gradient GEMMs read.
+//
+// Mainloop, pipeline, descriptors and the three-accumulator 3xTF32 scheme are those of tc_grouped.cuh.
+//
+// STATUS: written after the round-1 GPU budget was spent — compiles, never run.  Opt-in (PPB_FUSED_CELL=1).
+#pragma once
+#include "tc_grouped.cuh"
+
+namespace tcl {
+
+using namespace tc;
+
+struct Step {                 // one (time step t >= 1, sub-batch) segment
+  tcg::Operand a;             // h image, rows of the segment at step t-1 (K-major, row0 = previous row origin)
+  tcg::Operand b;             // gate-interleaved W_hh image (K-major, 4H rows, H columns)
+  int M;                      // segment rows, padded to 128
+  int H, S;                   // hidden size (reduction length; N = 4H), sample-embedding width (<= 8)
+  int row0;                   // first global row of the segment at step t (multiple of 128)
+  int tile_start, tiles_m, tiles_n;
+  const float* p_obs;         // [traces, 4H]  observation projection (+0), original gate-major columns
+  const float* p_step;        // [steps, 4H]   step-embedding projection + both biases
+  const float* smp_emb;       // [rows, S]     previous-sample embedding of every row
+  const float* w_smp_t;       // [S, 4H]       W_ih columns of the sample embedding, transposed
+  const int* row_trace;       // [rows] trace of a row, -1 for padding rows
+  const int* row_step;        // [rows] step (segment) id of a row
+  const int* row_prev;        // [rows] row of the same trace at step t-1
+  float* gates;               // [rows, 4H] activated gates (i,f,g,o), gate-major columns — read by the backward pass
+  float* c;                   // [rows, H]
+  float* h;                   // [rows, H]
+  float* hk_hi; float* hk_lo; float* hmn_hi; float* hmn_lo;   // tile images of h (both formats)
+  int hkb;                    // column blocks of the h images (H / 32)
+};
+
+struct __align__(1024) Smem {
+  float a_hi[tcg::kStages][kTileFloats];
+  float a_lo[tcg::kStages][kTileFloats];
+  float b_hi[tcg::kStages][kTileFloats];
+  float b_lo[tcg::kStages][kTileFloats];
+  uint64_t full[tcg::kStages];
+  uint64_t empty[tcg::kStages];
+  uint64_t tmem_full;
+  uint32_t tmem_base;
+  Step step;
+};
+static_assert(tcg::kEpiWarps * 32 * 33 * 4 <= 2 * tcg::kStages * kTileBytes, "staging blocks must fit in the A stages");
+
+__device__ __forceinline__ void quad_barrier(int q) {  // the four epilogue warps that share TMEM lane quadrant q
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(128) : "memory");
+}
+
+template <bool X3>
+__global__ void __launch_bounds__(tcg::kThreads, 1) k_lstm_step(const Step* __restrict__ steps, int n_steps) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  int lo_i = 0, hi_i = n_steps - 1;
+  while (lo_i < hi_i) {
+    int mid = (lo_i + hi_i + 1) >> 1;
+    if (steps[mid].tile_start <= tile) lo_i = mid; else hi_i = mid - 1;
+  }
+  for (int i = threadIdx.x; i < (int)(sizeof(Step) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(&sm.step)[i] = reinterpret_cast<const uint32_t*>(steps + lo_i)[i];
+  __syncthreads();
+  const Step& P = sm.step;
+  const int local = tile - P.tile_start;
+  const int mt = local / P.tiles_n, nt = local % P.tiles_n;   // nt = block of 32 hidden units
+  const int KC = (P.H + 31) / 32;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < tcg::kStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+    mbar_init(&sm.tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<tcg::kTmemCols>(&sm.tmem_base);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t bytes = (tcg::stage_bytes(P.a, mt) + tcg::stage_bytes(P.b, nt)) * (X3 ? 2u : 1u);
+      for (int c = 0; c < KC; ++c) {
+        int s = c % tcg::kStages;
+        uint32_t ph = (c / tcg::kStages) & 1;
+        mbar_wait(&sm.empty[s], ph ^ 1);
+        mbar_expect_tx(&sm.full[s], bytes);
+        tcg::load_operand(P.a, mt, c, sm.a_hi[s], sm.a_lo[s], X3, &sm.full[s]);
+        tcg::load_operand(P.b, nt, c, sm.b_hi[s], sm.b_lo[s], X3, &sm.full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(128, tcg::kBN, 0, 0);
+      for (int c = 0; c < KC; ++c) {
+        int s = c % tcg::kStages;
+        uint32_t ph = (c / tcg::kStages) & 1;
+        mbar_wait(&sm.full[s], ph);
+        fence_after_sync();
+        uint32_t sa_hi = smem_u32(sm.a_hi[s]), sa_lo = smem_u32(sm.a_lo[s]);
+        uint32_t sb_hi = smem_u32(sm.b_hi[s]), sb_lo = smem_u32(sm.b_lo[s]);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint64_t ah = tcg::operand_desc(false, sa_hi, ks), bh = tcg::operand_desc(false, sb_hi, ks);
+          if (X3) {
+            uint64_t al = tcg::operand_desc(false, sa_lo, ks), bl = tcg::operand_desc(false, sb_lo, ks);
+            mma_tf32(tmem + 2 * tcg::kBN, al, bh, idesc, (c == 0 && ks == 0) ? 0u : 1u);
+            mma_tf32(tmem + 2 * tcg::kBN, ah, bl, idesc, 1u);
+            mma_tf32(tmem + (c & 1) * tcg::kBN, ah, bh, idesc, (c < 2 && ks == 0) ? 0u : 1u);
+          } else {
+            mma_tf32(tmem, ah, bh, idesc, (c == 0 && ks == 0) ? 0u : 1u);
+          }
+        }
+        mma_commit(&sm.empty[s]);
+      }
+      mma_commit(&sm.tmem_full);
+    }
+  } else {
+    const int q = warp & 3;              // TMEM lane quadrant = 32-row block of the tile
+    const int g = (warp - 2) >> 2;       // 32-column chunk of the tile = gate (i, f, g, o)
+    const int qi = (warp - 2) & 3;       // position of this quadrant's warp inside every group of four staging blocks
+    float (*stg)[33] = reinterpret_cast<float (*)[33]>(reinterpret_cast<float*>(sm.a_hi) + (warp - 2) * 32 * 33);
+    mbar_wait(&sm.tmem_full, 0);
+    fence_after_sync();
+    const int H = P.H, H4 = 4 * P.H, S = P.S;
+    const int u = nt * 32 + lane;        // hidden unit owned by this lane
+    const int col = g * H + u;           // its column in the gate-major [.., 4H] arrays
+    float v[32];
+    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + g * 32, v);
+    if (X3) {
+      float w[32];
+      if (KC > 1) {
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + tcg::kBN + g * 32, w);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += w[j];
+      }
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 2 * tcg::kBN + g * 32, w);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += w[j];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) stg[lane][j] = v[j];   // thread = row  ->  lane = column
+    __syncwarp();
+    float wsmp[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) wsmp[s] = (s < S) ? __ldg(P.w_smp_t + (int64_t)s * H4 + col) : 0.0f;
+    const int64_t row_base = (int64_t)P.row0 + mt * 128 + q * 32;
+    // ---- phase 1: this warp's gate for its 32 rows ------------------------------------------------------------------
+    for (int r = 0; r < 32; ++r) {
+      const int64_t row = row_base + r;
+      const int tr = __ldg(P.row_trace + row);
+      float act = 0.0f;
+      if (tr >= 0) {   // warp-uniform
+        const int st = __ldg(P.row_step + row);
+        // same order of additions as k_cell_fwd: (P_obs + P_step) + recurrent, then the sample-embedding FMAs
+        float x = __ldg(P.p_obs + (int64_t)tr * H4 + col) + __ldg(P.p_step + (int64_t)st * H4 + col);
+        x += stg[r][lane];
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          if (s < S) x = fmaf(__ldg(P.smp_emb + row * S + s), wsmp[s], x);
+        act = (g == 2) ? tanhf(x) : 1.0f / (1.0f + expf(-x));
+      }
+      tcg::st_global(P.gates + row * H4 + col, act);
+      stg[r][lane] = act;
+    }
+    quad_barrier(q);
+    // ---- phase 2: cell update, 8 rows per warp; the four gates come from the four staging blocks of the quadrant --------
+    float (*sg_i)[33] = reinterpret_cast<float (*)[33]>(reinterpret_cast<float*>(sm.a_hi) + (0 * 4 + qi) * 32 * 33);
+    float (*sg_f)[33] = reinterpret_cast<float (*)[33]>(reinterpret_cast<float*>(sm.a_hi) + (1 * 4 + qi) * 32 * 33);
+    float (*sg_g)[33] = reinterpret_cast<float (*)[33]>(reinterpret_cast<float*>(sm.a_hi) + (2 * 4 + qi) * 32 * 33);
+    float (*sg_o)[33] = reinterpret_cast<float (*)[33]>(reinterpret_cast<float*>(sm.a_hi) + (3 * 4 + qi) * 32 * 33);
+    const int64_t hkb = P.hkb;
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+      const int r = g * 8 + rr;
+      const int64_t row = row_base + r;
+      const int tr = __ldg(P.row_trace + row);
+      float cn = 0.0f, hn = 0.0f;
+      if (tr >= 0) {
+        const int64_t rp = __ldg(P.row_prev + row);
+        const float cp = tcg::ld_global(P.c + rp * H + u);
+        cn = sg_f[r][lane] * cp + sg_i[r][lane] * sg_g[r][lane];
+        hn = sg_o[r][lane] * tanhf(cn);
+      }
+      tcg::st_global(P.c + row * H + u, cn);
+      tcg::st_global(P.h + row * H + u, hn);
+      // image position of (row, u): tile (row / 128, nt), row span of 32 floats, swizzled chunk
+      const int64_t span = ((row >> 7) * hkb + nt) * kTileFloats + (row & 127) * 32;
+      float hh, hl;
+      split_tf32(hn, hh, hl);
+      const int64_t pos_k = span + ((((lane >> 2) ^ (int)(row & 7))) << 2) + (lane & 3);
+      tcg::st_global(P.hk_hi + pos_k, hh);
+      tcg::st_global(P.hk_lo + pos_k, hl);
+      const int64_t pos_mn = span + ((((lane >> 3) ^ (int)(row & 3))) << 3) + (lane & 7);
+      tcg::st_global(P.hmn_hi + pos_mn, hh);
+      tcg::st_global(P.hmn_lo + pos_mn, hl);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after_sync();
+    tmem_dealloc<tcg::kTmemCols>(tmem);
+  }
+}
+
+inline size_t smem_bytes() { return sizeof(Smem) + 1024; }
+
+// W_hh [4H, H] (row-major, gate-major rows) -> K-format hi / lo tile image with gate-interleaved rows
+__global__ void __launch_bounds__(256) k_pack_whh_interleaved(const float* __restrict__ w_hh, int H,
+                                                               float* __restrict__ img_hi, float* __restrict__ img_lo) {
+  const int kb = H / 32;
+  const int rt = blockIdx.x;             // packed row tile = block of 32 hidden units
+  for (int qi = threadIdx.x + blockIdx.y * blockDim.x; qi < 128 * kb * 8; qi += blockDim.x * gridDim.y) {
+    const int c16 = qi & 7, t = qi >> 3;
+    const int cb = t % kb, r = t / kb;   // r = packed row inside the tile = gate * 32 + j
+    const int src_row = (r >> 5) * H + rt * 32 + (r & 31);
+    const int k0 = cb * 32 + c16 * 4;
+    float h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_tf32(__ldg(w_hh + (int64_t)src_row * H + k0 + j), h[j], l[j]);
+    const int64_t o = ((int64_t)rt * kb + cb) * kTileFloats + r * 32 + ((c16 ^ (r & 7)) << 2);
+    *reinterpret_cast<float4*>(img_hi + o) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(img_lo + o) = make_float4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+}  // namespace tcl
