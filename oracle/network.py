@@ -169,3 +169,59 @@ def loss_and_grads(params, sub_batches, observe_names, observe_in_dims, K):
     value.backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in p.items()}
     return value.detach(), grads, [x.detach() for x in lps]
+
+
+def head_params(params, address, family, K, h, prior0, prior1):
+    """Proposal parameters a head returns at inference time (proposal_*.py forward, the same transforms as
+    head_log_prob): mixtures -> (means, stddevs, probs) each [n, K]; Categorical -> probs [n, C]."""
+    x = _ff(h, params, '_layers_proposal.{}._ff'.format(address), False)
+    if family == 'Categorical':
+        return (torch.softmax(x, dim=1) + 1e-8,)
+    means, stddevs, coeffs = x[:, :K], x[:, K:2 * K], torch.softmax(x[:, 2 * K:], dim=1)
+    p0 = torch.as_tensor(prior0, dtype=torch.float32).reshape(-1, 1)
+    p1 = torch.as_tensor(prior1, dtype=torch.float32).reshape(-1, 1)
+    if family == 'Normal':
+        return p0 + means * p1, torch.exp(stddevs) * p1, coeffs
+    if family == 'Uniform':
+        rng = p1 - p0
+        return p0 + torch.sigmoid(means) * rng, rng / 1000 + torch.sigmoid(stddevs) * rng * 10, coeffs
+    if family == 'Poisson':
+        return torch.sigmoid(means) * 40.0, torch.exp(stddevs), coeffs
+    raise RuntimeError('unsupported family ' + family)
+
+
+def infer_sequence(params, obs_row, observe_names, observe_in_dims, K, steps, n=1):
+    """InferenceNetworkLSTM._infer_init + _infer_step replayed over one address sequence
+    (pyprob/nn/inference_network.py:141-148, pyprob/nn/inference_network_lstm.py:82-134).
+
+    steps: list of dicts {address, family, num_categories, prior0, prior1, prev_value} where prev_value is the value
+    ([n] tensor) drawn at the PREVIOUS step (ignored at the first step).  All n particles share the observation.
+    Returns one tuple of proposal parameters per step (see head_params)."""
+    obs_emb = embed_observe(params, obs_row.reshape(1, -1).float(), observe_names, observe_in_dims).expand(n, -1)
+    W_ih, W_hh = params['_layers_lstm.weight_ih_l0'], params['_layers_lstm.weight_hh_l0']
+    b_ih, b_hh = params['_layers_lstm.bias_ih_l0'], params['_layers_lstm.bias_hh_l0']
+    H = W_hh.size(1)
+    h, c = torch.zeros(n, H), torch.zeros(n, H)
+    smp_dim = next(v.size(0) for k, v in params.items() if k.startswith('_layers_sample_embedding.') and
+                   k.endswith('.bias'))
+    out = []
+    for t, st in enumerate(steps):
+        cur_t = params['_layers_distribution_type_embedding.' + st['family']]
+        cur_a = params['_layers_address_embedding.' + st['address']]
+        if t == 0:
+            smp = torch.zeros(n, smp_dim)
+            prev_t, prev_a = torch.zeros_like(cur_t), torch.zeros_like(cur_a)
+        else:
+            pv = steps[t - 1]
+            smp = sample_embedding(params, pv['address'], pv['family'], pv['num_categories'],
+                                   torch.as_tensor(st['prev_value'], dtype=torch.float32).reshape(-1))
+            prev_t = params['_layers_distribution_type_embedding.' + pv['family']]
+            prev_a = params['_layers_address_embedding.' + pv['address']]
+        x = torch.cat([obs_emb, smp, torch.cat([prev_t, prev_a, cur_t, cur_a]).expand(n, -1)], dim=1)
+        g = x @ W_ih.t() + b_ih + h @ W_hh.t() + b_hh
+        i, f, gg, o = (torch.sigmoid(g[:, :H]), torch.sigmoid(g[:, H:2 * H]), torch.tanh(g[:, 2 * H:3 * H]),
+                       torch.sigmoid(g[:, 3 * H:]))
+        c = f * c + i * gg
+        h = o * torch.tanh(c)
+        out.append(head_params(params, st['address'], st['family'], K, h, st['prior0'], st['prior1']))
+    return out
