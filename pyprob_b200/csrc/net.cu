@@ -69,8 +69,10 @@ struct ppb_net {
   int fused_cell = 0;
   float* whh_il = nullptr;          // gate-interleaved K-format image of W_hh: hi part, then lo part
   int64_t whh_il_floats = 0;        // floats per part
-  void* d_lstm_steps = nullptr;     // device list of tcl::Step
+  void* d_lstm_steps = nullptr;     // device list of tcl::Step (level 1) or tcl::Seq + row_off (level 2)
   size_t lstm_steps_cap = 0;        // bytes
+  int* d_lstm_progress = nullptr;   // level 2: arrival counters (one per 128-row tile) + error flag
+  int lstm_progress_cap = 0;        // ints
   // pinned staging ring for problem lists
   Problem* h_stage[2] = {nullptr, nullptr};
   cudaEvent_t ev_stage[2] = {nullptr, nullptr};
@@ -814,7 +816,7 @@ int ppb_net_create(ppb_net** out, const ppb_net_desc* d) {
   n->desc = *d;
   n->I = d->obs_dim + d->sample_dim + 2 * (d->type_dim + d->addr_dim);
   const char* fc = getenv("PPB_FUSED_CELL");
-  n->fused_cell = (fc && fc[0] == '1') ? 1 : 0;
+  n->fused_cell = (fc && (fc[0] == '1' || fc[0] == '2')) ? fc[0] - '0' : 0;   // 1: per-step launches, 2: persistent
   *out = n;
   return PPB_OK;
 }
@@ -859,6 +861,7 @@ int ppb_net_destroy(ppb_net* net) {
   if (net->d_pack) cudaFree(net->d_pack);
   if (net->whh_il) cudaFree(net->whh_il);
   if (net->d_lstm_steps) cudaFree(net->d_lstm_steps);
+  if (net->d_lstm_progress) cudaFree(net->d_lstm_progress);
   delete net;
   return PPB_OK;
 }

@@ -1,6 +1,6 @@
 """A/B timing of the opt-in kernels against the defaults, each arm in its own process (the switches are read from
 the environment when the library / network handle is created):
-  PPB_FUSED_CELL=1     synthetic 50-address training step (B=512), forward+backward+Adam, CUDA events
+  PPB_FUSED_CELL=1|2   synthetic 50-address training step (B=512), forward+backward+Adam, CUDA events
   PPB_MIXTURE_STAGED=1 mixture-of-Normals / mixture-of-TruncatedNormals log_prob at 2^24 particles, K=10
 Prints one JSON object.  Timings only — correctness is the job of tests/test_fused_cell_gpu.py and
 tests/test_scoring_staged_gpu.py."""
@@ -86,6 +86,7 @@ def run(script, env_extra):
 
 
 if __name__ == '__main__':
-    print(json.dumps({'synthetic50_step': {'default': run(_STEP, {}), 'fused_cell': run(_STEP, {'PPB_FUSED_CELL': '1'})},
+    print(json.dumps({'synthetic50_step': {'default': run(_STEP, {}), 'fused_cell': run(_STEP, {'PPB_FUSED_CELL': '1'}),
+                                           'persistent': run(_STEP, {'PPB_FUSED_CELL': '2'})},
                       'mixture_scoring': {'default': run(_MIX, {}), 'staged': run(_MIX, {'PPB_MIXTURE_STAGED': '1'})}},
                      indent=1))

@@ -1,4 +1,4 @@
-"""Opt-in LSTM step with the cell fused into the recurrent GEMM epilogue (csrc/tc_lstm.cuh, PPB_FUSED_CELL=1): same
+"""Opt-in LSTM steps with the cell fused into the recurrent GEMM epilogue (csrc/tc_lstm.cuh, PPB_FUSED_CELL=1|2): same
 GEMM accumulation order, same order of additions, same activations as the unfused pair (tcg::k_grouped + k_cell_fwd),
 so loss and every gradient must come out bit-identical; and it must agree with the oracle like the default path."""
 import numpy as np
@@ -23,20 +23,21 @@ def _case(seed, lstm_dim, spec, precision):
     return net, subs
 
 
+@pytest.mark.parametrize('level', ['1', '2'])   # 1: one fused launch per time step, 2: one persistent launch for all steps
 @pytest.mark.parametrize('precision', [0, 1])
 @pytest.mark.parametrize('seed,lstm_dim,spec', [
     (2, 32, [([0, 1, 2, 3, 4, 5], 7), ([2], 1), ([0, 3], 64), ([1, 5, 4, 0], 3)]),
     (3, 64, [([2, 4], 130), ([5, 1, 5, 1, 5, 1, 0], 33), ([3], 257)]),
     (4, 128, [([0, 1, 2, 3, 4, 5, 0, 1, 2, 3], 300)]),
 ])
-def test_fused_cell_is_bit_identical_to_the_unfused_step(cuda, monkeypatch, seed, lstm_dim, spec, precision):
+def test_fused_cell_is_bit_identical_to_the_unfused_step(cuda, monkeypatch, seed, lstm_dim, spec, precision, level):
     monkeypatch.delenv('PPB_FUSED_CELL', raising=False)
     base, subs = _case(seed, lstm_dim, spec, precision)
     ok, loss0 = base._loss(synthetic.ArrayBatch(subs))
     assert ok
     loss0.backward()
     g0 = base._arena.grad.clone()
-    monkeypatch.setenv('PPB_FUSED_CELL', '1')      # read when the native network handle is created
+    monkeypatch.setenv('PPB_FUSED_CELL', level)    # read when the native network handle is created
     fused, _ = _case(seed, lstm_dim, spec, precision)
     ok, loss1 = fused._loss(synthetic.ArrayBatch(subs))
     assert ok
