@@ -352,7 +352,9 @@ __global__ void __launch_bounds__(tcg::kThreads, 1) k_lstm_seq(const Seq* __rest
       cell_epilogue<X3>(reinterpret_cast<float*>(sm.a_hi), P.io, tmem, warp, lane, KC, nt, (int64_t)row0 + mt * 128);
       __threadfence();   // this thread's h / c / image stores are visible device-wide before the arrival below
     }
-    // the accumulators are drained and the staging blocks (aliasing the operand stages) are free again
+    // the accumulators are drained and the staging blocks (aliasing the operand stages) are free again; the next
+    // step's bulk copies (async proxy) overwrite shared memory this step's epilogue wrote through the generic proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
