@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kThreads) k_mixture(const float* __restrict__ 
 // of its tile with coalesced 128-bit loads, then every thread reads its own row from shared memory (instead of 3K
 // strided 4-byte global loads per thread).  Requires densely packed rows (row_stride == K) and 16-byte aligned
 // arrays.  STATUS: opt-in (PPB_MIXTURE_STAGED=1) until its first hardware run — written after the round-1 GPU budget
-// was spent; results must be bit-identical to k_mixture.
+// was spent; results must equal k_mixture's to rounding.
 template <int KMAX, bool TRUNC>
 __global__ void __launch_bounds__(kThreads) k_mixture_staged(const float* __restrict__ value,
                                                               const float* __restrict__ means,
