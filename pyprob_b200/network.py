@@ -507,11 +507,6 @@ class InferenceNetworkLSTM(nn.Module):
         """Device tables of the segment-aware optimiser step (ppb_optimizer_step_segmented): one segment per parameter
         tensor of the reference.  Needed for LARC / SGD (per-tensor norms, per-tensor first-step flag) and for the
         reference's skipping of tensors whose gradient is absent from a minibatch (`_skip_absent_gradients`)."""
-        if os.environ.get('PPB_RUN_UNVALIDATED') != '1':
-            raise NotImplementedError(
-                'pyprob_b200: Optimizer.{} runs on the segment-aware optimiser kernels (csrc/optim.cu), which have not '
-                'been validated on hardware yet; set PPB_RUN_UNVALIDATED=1 to use them, or train with Optimizer.ADAM'
-                .format(self._optimizer_type.name))
         names = sorted(self.parameter_index, key=lambda k: self.parameter_index[k][0])
         n = self._arena.numel()
         seg_of_block = np.full((n + 3) // 4, -1, dtype=np.int32)

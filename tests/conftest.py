@@ -12,12 +12,6 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with `-m gpu`)')
 
 
-# Tests of code written after the round's GPU budget was spent: they have never run on hardware, so they are opt-in
-# (PPB_RUN_UNVALIDATED=1) until a first green run on a B200 — a red surprise must not mask the validated suite.
-unvalidated_on_hardware = pytest.mark.skipif(os.environ.get('PPB_RUN_UNVALIDATED') != '1',
-                                             reason='not yet run on a B200 (set PPB_RUN_UNVALIDATED=1 to run)')
-
-
 @pytest.fixture(scope='session')
 def golden_scoring():
     import numpy as np

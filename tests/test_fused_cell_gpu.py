@@ -8,9 +8,8 @@ import torch
 
 from oracle import network as onet
 from pyprob_b200 import synthetic
-from tests.conftest import unvalidated_on_hardware
 
-pytestmark = [pytest.mark.gpu, unvalidated_on_hardware]
+pytestmark = pytest.mark.gpu
 
 TABLE = [('a_u', 'Uniform', 0), ('a_c', 'Categorical', 5), ('a_n', 'Normal', 0), ('a_p', 'Poisson', 0),
          ('a_n2', 'Normal', 0), ('a_c2', 'Categorical', 3)]

@@ -5,10 +5,9 @@ import pytest
 import torch
 
 from pyprob_b200 import synthetic
-from tests.conftest import unvalidated_on_hardware
 from tests.test_oracle_infer import load_infer_golden
 
-pytestmark = [pytest.mark.gpu, unvalidated_on_hardware]
+pytestmark = pytest.mark.gpu
 
 
 def _network(fx, precision):

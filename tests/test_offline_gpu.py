@@ -11,9 +11,8 @@ import pyprob_b200 as pyprob
 from pyprob_b200 import InferenceEngine, InferenceNetwork, Model
 from pyprob_b200.distributions import Normal, Uniform
 from pyprob_b200.offline import OfflineDataset
-from tests.conftest import unvalidated_on_hardware
 
-pytestmark = [pytest.mark.gpu, unvalidated_on_hardware]
+pytestmark = pytest.mark.gpu
 
 
 class GaussianUnknownMean(Model):

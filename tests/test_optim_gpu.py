@@ -9,9 +9,8 @@ import pytest
 import torch
 
 from oracle import optim as ooptim
-from tests.conftest import unvalidated_on_hardware
 
-pytestmark = [pytest.mark.gpu, unvalidated_on_hardware]
+pytestmark = pytest.mark.gpu
 
 SIZES = [35, 5, 12, 4, 16, 3, 70001, 130]     # parameter tensors; regions start on multiples of 4, ragged tail
 KINDS = {'adam': 0, 'adam_larc': 1, 'sgd': 2, 'sgd_larc': 3}
@@ -108,7 +107,6 @@ def test_adam_larc_trains_through_the_public_api(cuda, monkeypatch):
             pyprob.observe(Normal(mu, math.sqrt(2)), name='obs1')
             return mu
 
-    monkeypatch.setenv('PPB_RUN_UNVALIDATED', '1')
     pyprob.seed(2)
     model = GaussianUnknownMean()
     model.learn_inference_network(num_traces=256 * 30, inference_network=InferenceNetwork.LSTM,

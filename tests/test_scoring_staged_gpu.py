@@ -7,9 +7,8 @@ import sys
 import numpy as np
 import pytest
 
-from tests.conftest import unvalidated_on_hardware
 
-pytestmark = [pytest.mark.gpu, unvalidated_on_hardware]
+pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
