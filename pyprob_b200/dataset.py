@@ -7,7 +7,7 @@
 import numpy as np
 import torch
 
-from .distributions import Categorical, Normal, Uniform
+from .distributions import Categorical, Normal, Uniform, set_shard_first_index
 from .encoding import EncodedBatch, SubBatch
 from .util import PriorInflation, TraceMode
 
@@ -118,6 +118,13 @@ class TraceBatch:
         return subs
 
 
+def rank_first_index(batch_size):
+    """Global Philox index of this rank's first trace within one distributed minibatch draw."""
+    from . import parallel
+    world, rank = parallel.world_info()
+    return rank * int(batch_size) if world > 1 else 0
+
+
 class OnlineDataset:
     def __init__(self, model, length=None, prior_inflation=PriorInflation.DISABLED):
         self._model = model
@@ -129,8 +136,17 @@ class OnlineDataset:
         return self._length
 
     def next_batch(self, batch_size):
-        trace = self._model._run_batched(batch_size, trace_mode=TraceMode.PRIOR_FOR_INFERENCE_NETWORK,
-                                         prior_inflation=self._prior_inflation)
+        """One minibatch of prior traces.  Under torch.distributed every rank draws a DISJOINT index range of the same
+        Philox stream (rank r takes particles [r * batch_size, (r + 1) * batch_size) of this draw), so that the world's
+        minibatches together are one global batch of world * batch_size independent traces — the reference's ranks draw
+        independently because each process seeds its own torch generator (inference_network.py:296-333)."""
+        first = rank_first_index(batch_size)
+        set_shard_first_index(first)
+        try:
+            trace = self._model._run_batched(batch_size, trace_mode=TraceMode.PRIOR_FOR_INFERENCE_NETWORK,
+                                             prior_inflation=self._prior_inflation)
+        finally:
+            set_shard_first_index(0)
         return TraceBatch(trace)
 
     def example_trace(self):

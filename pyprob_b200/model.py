@@ -79,7 +79,7 @@ class Model:
             try:
                 trace = self._run_batched(n, init=False, *args, **kwargs)
             except (ValueError, RuntimeError) as e:
-                if n > 1 and 'convert' in str(e) and 'calar' in str(e):
+                if n > 1 and (('convert' in str(e) and 'calar' in str(e)) or 'ambiguous' in str(e)):
                     warnings.warn('Model uses python-scalar control flow on sampled values; running one particle per '
                                   'execution (slow). Use pyprob_b200.while_loop for lock-step loops.')
                     self._scalar_mode, chunk = True, 1

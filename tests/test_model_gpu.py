@@ -131,3 +131,22 @@ def test_marsaglia_inference_compilation(cuda):
                                    observe={'obs0': 8, 'obs1': 9})
     assert abs(float(post.mean) - TRUE_MEAN) < 0.5
     assert post.effective_sample_size > 0.016 * 8192  # reference floor: tests/test_inference.py:344
+
+
+def test_online_minibatches_are_disjoint_between_ranks(cuda, monkeypatch):
+    """Data-parallel online training: rank r draws particles [r*B, (r+1)*B) of one Philox draw, so two ranks' minibatches
+    are the two halves of a single 2B-trace batch — never the same traces twice."""
+    from pyprob_b200 import parallel
+    from pyprob_b200.dataset import OnlineDataset
+    model = GaussianUnknownMean()
+    halves = []
+    for rank in (0, 1):
+        pyprob.seed(9)
+        monkeypatch.setattr(parallel, 'world_info', lambda r=rank: (2, r))
+        batch = OnlineDataset(model).next_batch(64)
+        halves.append(batch.trace.variables_controlled[0].value.cpu())
+    assert not torch.equal(halves[0], halves[1])
+    pyprob.seed(9)
+    monkeypatch.setattr(parallel, 'world_info', lambda: (1, 0))
+    full = OnlineDataset(model).next_batch(128).trace.variables_controlled[0].value.cpu()
+    assert torch.equal(torch.cat(halves), full)

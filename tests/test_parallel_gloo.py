@@ -45,7 +45,8 @@ def _worker(rank, world, port, q):
     wg = np.random.default_rng(7).normal(-30, 4, n).astype(np.float32)
     part = torch.from_numpy(_triples(wg[first:first + count], 2048 if rank == 0 else 1000))
     allp = parallel.gather_weight_partials(part)
-    q.put((rank, local.numpy(), grad.numpy(), mean_loss, scale, first, count, allp.numpy()))
+    from pyprob_b200 import dataset
+    q.put((rank, local.numpy(), grad.numpy(), mean_loss, scale, first, count, allp.numpy(), dataset.rank_first_index(256)))
     dist.destroy_process_group()
 
 
@@ -66,6 +67,7 @@ def test_flat_allreduce_and_weight_partials_world2():
         assert abs(r[3] - 2.0) < 1e-6 and r[4] == 0.5             # mean loss, grad_scale = 1/world
     assert res[0][5] == 0 and res[0][5] + res[0][6] == res[1][5] and res[1][5] + res[1][6] == 10007
     np.testing.assert_array_equal(res[0][7], res[1][7])           # identical gathered list on both ranks
+    assert res[0][8] == 0 and res[1][8] == 256                    # online minibatches: disjoint Philox index ranges per rank
     wg = np.random.default_rng(7).normal(-30, 4, 10007).astype(np.float32)
     lse, ess, _ = oweights.finalize(wg)
     got_lse, got_ess = _combine(res[0][7])
