@@ -12,12 +12,17 @@ backward -> (N>1: one NCCL all-reduce of the flat gradient arena) -> fused Adam.
           H2D -> forward/backward/Adam -> D2H loss, every step
   roofline     : LSTM gate GEMM class (input projections + recurrent GEMMs, fwd+bwd), tensor-core bound
   cpu_baseline : the oracle port of the reference's _loss + backward + Adam on this box's host cores
-  extra        : IS / IC posterior particles/s through the public Model API (the metric's other half)
+  workloads    : the other BASELINE configurations, each with its own CPU baseline timed in the same run:
+                 IS posterior (GUM, 64k particles), IC posterior (GUM and GUM-Marsaglia, LSTM h=512, 64k particles) —
+                 the particles/s half of the metric — and the configs[3] shape (50 addresses, T=50, 512 traces per GPU)
+                 with the roofline of its gate-GEMM class
+  extra        : HBM rooflines of the scoring kernels, the gate GEMM at a saturating size
 
 `--impl reference` times the CPU oracle port (the reference cannot travel to the GPU box) on the same config.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -34,6 +39,21 @@ if ROOT not in sys.path:
 BATCH = 256
 LSTM_DIM = 512
 WORKLOAD = 'GaussianUnknownMean IC train, LSTM h=512, obs-embed 32+32, batch 256/GPU (BASELINE configs[1])'
+GUM_ADDRESS = '98__forward__mu__Normal__1'
+GUM_PARAMETERS = 1643583    # the reference's count for this configuration
+
+
+def workload_config(n_gpus):
+    """What is computed — identical on the b200 arm and on the reference arm for the same --gpus."""
+    return {'workload': WORKLOAD, 'global_batch': BATCH * n_gpus, 'batch_per_gpu': BATCH, 'lstm_dim': LSTM_DIM,
+            'trace_length': 1, 'observe_embeddings': 'obs0:32,obs1:32 (feed-forward, depth 2)', 'mixture_components': 10,
+            'parameters': GUM_PARAMETERS, 'optimizer': 'Adam lr 1e-3', 'arithmetic': 'fp32 results (1e-4 of the reference)'}
+
+
+def percentile_stats(ms):
+    a = np.sort(np.asarray(ms, dtype=np.float64))
+    return {'median': float(np.median(a)), 'p90': float(a[min(len(a) - 1, int(math.ceil(0.9 * len(a))) - 1)]),
+            'min': float(a[0]), 'max': float(a[-1])}
 
 
 def measured_peaks():
@@ -131,40 +151,26 @@ class ClockSampler:
 # ---- CPU arm: the oracle port of the reference path -------------------------------------------------------
 def cpu_reference_arm(steps, warmup, budget_s=20.0):
     """_loss + backward + Adam of the reference network (oracle restatement, torch CPU fp32, all host threads)
-    on GUM minibatches of 256 traces.  Returns traces/s over the timed steps."""
+    on GUM minibatches of 256 traces (four pre-generated minibatches cycled, like the GPU arm).  Returns traces/s."""
     from oracle import network as onet
+    from oracle import params as oparams
     from pyprob_b200 import synthetic
     threads = os.cpu_count() or 1
     rng = np.random.default_rng(0)
-    # parameters with the reference's names/shapes (built on the CPU without the CUDA library)
-    torch.manual_seed(0)
-    import torch.nn as nn
-    params = {}
-
-    def lin(prefix, i, o):
-        m = nn.Linear(i, o)
-        params[prefix + '.weight'], params[prefix + '.bias'] = m.weight.detach().clone(), m.bias.detach().clone()
-    for name in ('obs0', 'obs1'):
-        lin('_layers_observe_embedding.{}._layers.0'.format(name), 1, 16)
-        lin('_layers_observe_embedding.{}._layers.1'.format(name), 16, 32)
-    lin('_layers_observe_embedding_final._layers.0', 64, 64)
-    lin('_layers_observe_embedding_final._layers.1', 64, 64)
-    I = 64 + 4 + 144
-    lstm = nn.LSTM(I, LSTM_DIM, 1)
-    for k in ('weight_ih_l0', 'weight_hh_l0', 'bias_ih_l0', 'bias_hh_l0'):
-        params['_layers_lstm.' + k] = getattr(lstm, k).detach().clone()
-    a = '98__forward__mu__Normal__1'
-    params['_layers_address_embedding.' + a] = torch.randn(64)
-    params['_layers_distribution_type_embedding.Normal'] = torch.randn(8)
-    lin('_layers_sample_embedding.{}._layers.0'.format(a), 1, 4)
-    lin('_layers_proposal.{}._ff._layers.0'.format(a), LSTM_DIM, (LSTM_DIM + 30) // 2)
-    lin('_layers_proposal.{}._ff._layers.1'.format(a), (LSTM_DIM + 30) // 2, 30)
+    params = oparams.random_params([('obs0', 1, 32, 2), ('obs1', 1, 32, 2)], [(GUM_ADDRESS, 'Normal', 0)],
+                                   lstm_dim=LSTM_DIM, K=10, seed=0)
     plist = {k: v.requires_grad_(True) for k, v in params.items()}
     opt = torch.optim.Adam(list(plist.values()), lr=1e-3)
+    batches = []
+    for _ in range(4):
+        b = synthetic.gum_batch(rng, BATCH)
+        batches.append([{k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in sb.items()}
+                        for sb in b.subs])
+    it = [0]
 
     def one_step():
-        b = synthetic.gum_batch(rng, BATCH)
-        subs = [{k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in sb.items()} for sb in b.subs]
+        subs = batches[it[0] % 4]
+        it[0] += 1
         opt.zero_grad()
         loss, _ = onet.loss(plist, subs, ['obs0', 'obs1'], [1, 1], 10)
         loss.backward()
@@ -198,10 +204,22 @@ def cpu_reference_arm(steps, warmup, budget_s=20.0):
     dt = time.perf_counter() - t0
     return {'value': done * BATCH / dt, 'unit': 'traces/s', 'cores': threads, 'kind': 'port',
             'sample': '{} steps of _loss+backward+Adam on {}-trace GUM minibatches (oracle/network.py, torch CPU fp32, '
-                      '{} threads), {:.1f} s'.format(done, BATCH, threads, dt)}, dt / done
+                      '{} of {} host threads — the fastest setting for this small-GEMM step), {:.1f} s'.format(
+                          done, BATCH, threads, os.cpu_count(), dt)}, dt / done
+
+
+def log(msg):
+    """Progress on stderr (stdout carries exactly one JSON line)."""
+    sys.stderr.write('[bench {:7.1f}s] {}\n'.format(time.perf_counter() - _T0, msg))
+    sys.stderr.flush()
+
+
+_T0 = time.perf_counter()
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(300, repeat=True, file=sys.stderr)   # a stuck phase shows where it is stuck
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=50)
@@ -227,8 +245,9 @@ def main():
                           'unit': 'traces/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': warmup,
                           'ms_per_step': s_per_step * 1e3, 'higher_is_better': True, 'scaling': 'weak',
                           'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                          'config': {'workload': WORKLOAD, 'global_batch': BATCH, 'note': 'CPU oracle port of the '
-                                     'reference path; rank 0 only'},
+                          'config': workload_config(args.gpus),
+                          'impl_config': {'note': 'CPU oracle port of the reference path (the Python reference cannot travel '
+                                          'to the GPU box); rank 0 only, one 256-trace minibatch per step whatever --gpus'},
                           'cpu_baseline': cb,
                           'e2e': {'value': cb['value'], 'unit': 'traces/s', 'h2d_bytes_per_step': 0,
                                   'd2h_bytes_per_step': 0}}))
@@ -305,9 +324,11 @@ def main():
         call('ppb_adam_step_dev', ptr(net._arena.data), ptr(grad), ptr(net._exp_avg), ptr(net._exp_avg_sq), nparams,
              ptr(hyper), ptr(adam_state), torch.cuda.current_stream().cuda_stream)
 
+    log('network built, {} parameters'.format(nparams))
     for i in range(warmup):
         device_step(i)
     barrier()
+    log('eager warm-up done')
     use_graph = not args.no_graph
     graphs = []
     if use_graph:  # the whole step (incl. the NCCL all-reduce for N > 1) replays from one CUDA graph per resident batch
@@ -329,12 +350,19 @@ def main():
             graphs[i % 4].replay()
         else:
             device_step(i)
+    log('graphs captured' if use_graph else 'no graph')
     sampler = ClockSampler(local_rank, getattr(torch.cuda.get_device_properties(dev), 'uuid', None))
     if rank == 0:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if peer is not None:
+        peer.phase_totals_us(reset=True)
     for i in range(args.steps):
         flush.zero_()                      # L2 flush between timed iterations (outside the timed spans)
+        if peer is not None:
+            # every rank starts the timed step at the same moment: the flush (not part of the step) must not leak its
+            # cross-rank skew into the span through the step's first cross-rank barrier
+            peer.rendezvous(stream.cuda_stream)
         ev[i][0].record(stream)
         run_step(i)
         ev[i][1].record(stream)
@@ -344,13 +372,16 @@ def main():
     device_step(0)
     torch.cuda.synchronize()
     launches = (_lib.call('ppb_launch_count') - l0) * args.steps
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    dev_ms = sum(step_ms)
+    dp_phases = peer.phase_totals_us() if peer is not None else None
     t = torch.tensor([dev_ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
     value = args.steps * BATCH * world / (dev_ms * 1e-3)
 
+    log('device-resident: {:.4f} ms/step'.format(dev_ms / args.steps))
     # ---- e2e: C-ABI host-buffer call, H2D + D2H inside the timed region --------------------------------------
     loss_host = torch.zeros(1).pin_memory()
     status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
@@ -392,6 +423,7 @@ def main():
     if peer is not None and peer.timed_out():
         raise RuntimeError('fused data-parallel step: a cross-rank barrier timed out; the measurement is void')
 
+    log('e2e: {:.4f} ms/step'.format(e2e_ms / args.steps))
     # ---- roofline of the gate-GEMM class: per-launch durations from CUDA events inside the step ---------------
     peaks = measured_peaks()
     roof = None
@@ -407,47 +439,68 @@ def main():
         ms, n, fl = C.c_double(), C.c_int64(), C.c_double()
         call('ppb_prof_read', C.byref(ms), C.byref(n), C.byref(fl))
         call('ppb_prof_enable', 0)
-        tf32_peak = peaks['bf16_tflops_sustained'] / 2.0   # tf32 dense = 1/2 of the measured bf16 GEMM peak
+        # the gate-GEMM launches are timed one by one with CUDA events: the burst figure is the matching denominator
+        tf32_peak = peaks['bf16_tflops'] / 2.0   # tf32 dense = 1/2 of the measured bf16 GEMM peak
         achieved = fl.value / (ms.value * 1e-3) / 1e12 if ms.value > 0 else 0.0
+        issue = 3.0 if args.precision == 0 else 1.0
         roof = {'bound': 'tensor', 'kernel': 'LSTM gate GEMM class (P_obs/P_step/recurrent + their dX/dW)',
                 'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': achieved / tf32_peak,
-                'traffic': None, 'launches': n.value, 'avg_launch_us': ms.value * 1e3 / max(n.value, 1),
+                'frac_issued_mma': achieved * issue / tf32_peak,
+                'traffic': committed_traffic('gate_gemm_configs1'), 'launches': n.value,
+                'avg_launch_us': ms.value * 1e3 / max(n.value, 1),
                 'flops_per_step': fl.value / max(prof_steps, 1),
-                'peak_source': '{} bf16_tflops_sustained / 2 (tf32)'.format(peaks['source'])}
+                'peak_source': '{} bf16_tflops (burst) / 2 = tf32 dense'.format(peaks['source']),
+                'note': 'achieved counts each product once; in 3xTF32 mode the tensor pipe issues 3 MMAs per product '
+                        '(frac_issued_mma). T = 1 at configs[1]: three 67-MFLOP GEMMs per step, launch-bound by construction; '
+                        'see workloads.ic_train_synthetic50_b512.roofline for the T = 50 recurrence'}
 
     extra = {}
+    workloads = {}
     cpu_baseline = None
     if rank == 0 and world == 1:
+        log('cpu baseline ...')
         cpu_baseline, _ = cpu_reference_arm(10 ** 6, 2, budget_s=args.cpu_budget)
+        log('cpu baseline: {:.0f} traces/s'.format(cpu_baseline['value']))
         if not args.no_extra:
             # secondary workloads: a failure here must not cost the headline line
-            for key, fn in (('posterior', lambda: posterior_extras(dev)),
-                            ('scoring_hbm_roofline', lambda: scoring_rooflines(dev, peaks)),
+            for key, fn in (('is_posterior_gum_n65536', lambda: posterior_is_workload(dev)),
+                            ('ic_posterior_gum_n65536', lambda: posterior_ic_gum_workload(dev)),
+                            ('ic_posterior_marsaglia_n65536', lambda: posterior_ic_marsaglia_workload(dev)),
+                            ('ic_train_synthetic50_b512', lambda: synthetic50_workload(dev, peaks))):
+                try:
+                    log('workload ' + key)
+                    workloads[key] = fn()
+                except Exception as exc:   # noqa: BLE001 - reported in the JSON line
+                    workloads[key] = {'error': '{}: {}'.format(type(exc).__name__, exc)}
+            for key, fn in (('scoring_hbm_roofline', lambda: scoring_rooflines(dev, peaks)),
                             ('gate_gemm_saturating_4096x2048x512', lambda: gate_gemm_saturating(dev, peaks))):
                 try:
-                    res = fn()
-                    if key == 'posterior':
-                        extra.update(res)
-                    else:
-                        extra[key] = res
-                except Exception as exc:   # noqa: BLE001 - reported in the JSON line
+                    log('extra ' + key)
+                    extra[key] = fn()
+                except Exception as exc:   # noqa: BLE001
                     extra[key + '_error'] = '{}: {}'.format(type(exc).__name__, exc)
             extra['hbm_peak_gbs'] = peaks['hbm_gbs']
     if rank == 0:
         out = {'metric': 'ic_train_traces_per_sec', 'value': value, 'unit': 'traces/s', 'n_gpus': world,
                'steps': args.steps, 'warmup': warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-               'config': {'workload': WORKLOAD, 'global_batch': BATCH * world, 'lstm_dim': LSTM_DIM, 'trace_length': 1,
-                          'parameters': nparams, 'parallelism': 'dp{}'.format(world),
-                          'collective': None if world == 1 else ('fused reduce-scatter+Adam+all-gather over NVLink '
-                                                                 'peer memory' if peer is not None else 'nccl all-reduce'),
-                          'precision': ['3xTF32', 'TF32', 'fp32-simt'][args.precision],
-                          'l2': 'flushed between timed steps (256 MiB memset outside the timed spans)',
-                          'cuda_graph': bool(use_graph)},
+               'config': workload_config(world),
+               'impl_config': {'arena_floats': nparams, 'parallelism': 'dp{}'.format(world),
+                               'collective': None if world == 1 else (
+                                   'fused reduce-scatter+Adam+all-gather over NVLink peer memory (ppb_dp_adam_step)'
+                                   if peer is not None else 'nccl all-reduce'),
+                               'precision': ['3xTF32', 'TF32', 'fp32-simt'][args.precision],
+                               'l2': 'flushed between timed steps (256 MiB memset outside the timed spans'
+                                     + ('; stream-ordered cross-rank rendezvous between flush and span' if peer is not None
+                                        else '') + ')',
+                               'cuda_graph': bool(use_graph)},
+               'ms_per_step_stats_rank0': percentile_stats(step_ms),
                'e2e': {'value': e2e_value, 'unit': 'traces/s', 'h2d_bytes_per_step': int(hosts[0].numel()),
                        'd2h_bytes_per_step': 8, 'ms_per_step': e2e_ms / args.steps},
                'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu_baseline,
-               'extra': extra}
+               'workloads': workloads, 'extra': extra}
+        if dp_phases is not None:
+            out['dp_step_phases_us_rank0'] = dp_phases
         print(json.dumps(out))
         sys.stdout.flush()
     if world > 1:
@@ -550,11 +603,35 @@ def gate_gemm_saturating(dev, peaks):
     return out
 
 
-def posterior_extras(dev):
-    """The metric's other half: IS / IC posterior particles/s through the public Model API (N = 1 only)."""
-    import math
+def committed_traffic(key):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of a kernel class from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json, written by scripts/summarise_ncu.py), or None."""
+    path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if not os.path.exists(path):
+        return None
+    try:
+        return json.load(open(path)).get(key, {}).get('dram_bytes_per_launch')
+    except Exception:   # noqa: BLE001
+        return None
+
+
+def _timed_cpu(fn, n_first, budget_s):
+    """Run fn(n) on growing particle counts until ~budget_s of CPU time is spent; returns (particles, seconds)."""
+    fn(max(n_first // 8, 4))   # warm-up
+    done, spent, n = 0, 0.0, n_first
+    while spent < budget_s:
+        t0 = time.perf_counter()
+        fn(n)
+        dt = time.perf_counter() - t0
+        done += n
+        spent += dt
+        n = int(min(max(n * (0.5 * budget_s / max(dt, 1e-3)), n), 8 * n))
+    return done, spent
+
+
+def _gum_model():
     import pyprob_b200 as pyprob
-    from pyprob_b200 import InferenceEngine, Model
+    from pyprob_b200 import Model
     from pyprob_b200.distributions import Normal
 
     class GUM(Model):
@@ -564,51 +641,83 @@ def posterior_extras(dev):
             pyprob.observe(lik, name='obs0')
             pyprob.observe(lik, name='obs1')
             return mu
+    return GUM()
+
+
+def _time_posterior(model, n, engine, reps):
+    obs = {'obs0': 8, 'obs1': 9}
+    for _ in range(2):
+        model.posterior_results(n, engine, observe=obs)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ess = 0.0
+    for _ in range(reps):
+        post = model.posterior_results(n, engine, observe=obs)
+        ess = float(post.effective_sample_size)   # device->host read of the result
+    torch.cuda.synchronize()
+    return reps * n / (time.perf_counter() - t0), ess
+
+
+def _cpu_entry(done, spent, what):
+    return {'value': done / spent, 'unit': 'particles/s', 'cores': 1, 'kind': 'port',
+            'sample': '{} particles, {:.1f} s: {} (oracle/posterior.py — one particle at a time like pyprob/model.py:59-60, '
+                      'without the reference\'s address extraction and Trace objects, i.e. faster than the reference)'.format(
+                          done, spent, what)}
+
+
+def posterior_is_workload(dev, budget_s=3.0):
+    """BASELINE configs[0] at north_star's size: GaussianUnknownMean, IMPORTANCE_SAMPLING from the prior, 64k particles
+    through Model.posterior_results (sample + 2 observe scores + fp64 weight normalisation + ESS read back)."""
+    import pyprob_b200 as pyprob
+    from oracle import posterior as opost
+    from pyprob_b200 import InferenceEngine
     pyprob.seed(1)
     pyprob.set_verbosity(0)
-    m = GUM()
-    out = {}
-    for n in (65536, 1 << 24):
-        for _ in range(3):
-            m.posterior_results(n, observe={'obs0': 8, 'obs1': 9})
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        reps = 5
-        for _ in range(reps):
-            post = m.posterior_results(n, observe={'obs0': 8, 'obs1': 9})
-            ess = post.effective_sample_size  # device->host read of the result
-        torch.cuda.synchronize()
-        out['is_posterior_particles_per_sec_n{}'.format(n)] = reps * n / (time.perf_counter() - t0)
-    # north_star's posterior case: GaussianUnknownMean, IC engine (LSTM h=512), 64k particles
+    m = _gum_model()
+    value, ess = _time_posterior(m, 65536, InferenceEngine.IMPORTANCE_SAMPLING, 10)
+    big, _ = _time_posterior(m, 1 << 24, InferenceEngine.IMPORTANCE_SAMPLING, 3)
+    done, spent = _timed_cpu(lambda n: opost.gum_is(n), 2000, budget_s)
+    cb = _cpu_entry(done, spent, 'prior draw + two Normal log_probs + float sum per particle')
+    return {'metric': 'is_posterior_particles_per_sec', 'value': value, 'unit': 'particles/s', 'particles': 65536,
+            'ess': ess, 'value_at_16M_particles': big, 'cpu_baseline': cb, 'ratio_to_cpu_baseline': value / cb['value'],
+            'config': 'GaussianUnknownMean, observe obs0=8 obs1=9, Model.posterior_results (BASELINE configs[0] at 64k)'}
+
+
+def posterior_ic_gum_workload(dev, budget_s=4.0):
+    """north_star's posterior case: GaussianUnknownMean, IMPORTANCE_SAMPLING_WITH_INFERENCE_NETWORK (LSTM h=512), 64k."""
     import contextlib
     import io
-    from pyprob_b200 import InferenceNetwork
+    import pyprob_b200 as pyprob
+    from oracle import posterior as opost
+    from pyprob_b200 import InferenceEngine, InferenceNetwork
+    pyprob.seed(2)
+    pyprob.set_verbosity(0)
+    m = _gum_model()
     with contextlib.redirect_stdout(io.StringIO()):
         m.learn_inference_network(num_traces=10 * 256, batch_size=256, inference_network=InferenceNetwork.LSTM,
                                   lstm_dim=512, observe_embeddings={'obs0': {'dim': 32}, 'obs1': {'dim': 32}})
-    n = 65536
-    eng = InferenceEngine.IMPORTANCE_SAMPLING_WITH_INFERENCE_NETWORK
-    for _ in range(2):
-        m.posterior_results(n, eng, observe={'obs0': 8, 'obs1': 9})
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    reps = 5
-    for _ in range(reps):
-        post = m.posterior_results(n, eng, observe={'obs0': 8, 'obs1': 9})
-        _ = post.effective_sample_size
-    torch.cuda.synchronize()
-    out['ic_posterior_gum_particles_per_sec_n65536'] = reps * n / (time.perf_counter() - t0)
-    out.update(ic_posterior_extra())
-    out.update(synthetic50_extra(dev))
-    return out
+    value, ess = _time_posterior(m, 65536, InferenceEngine.IMPORTANCE_SAMPLING_WITH_INFERENCE_NETWORK, 5)
+    net = m._inference_network
+    P = {k: v.cpu() for k, v in net.reference_state_dict().items()}
+    address = next(iter(net._addresses))
+    torch.set_num_threads(1)
+    done, spent = _timed_cpu(lambda n: opost.gum_ic(n, P, address), 100, budget_s)
+    cb = _cpu_entry(done, spent, 'observe embedding once, then per particle one LSTM step (h=512) + mixture proposal '
+                                 'draw + log p - log q + two observe scores')
+    return {'metric': 'ic_posterior_particles_per_sec', 'value': value, 'unit': 'particles/s', 'particles': 65536,
+            'ess': ess, 'cpu_baseline': cb, 'ratio_to_cpu_baseline': value / cb['value'],
+            'config': 'GaussianUnknownMean, LSTM h=512 proposal network (same weights on both sides), 64k particles'}
 
 
-def ic_posterior_extra():
-    """BASELINE configs[2] shape: GaussianUnknownMeanMarsaglia (stochastic control flow), IC posterior with 64k
-    particles through Model.posterior_results (lock-step while_loop; LSTM h=512).  Throughput does not depend on
-    how well the proposals are trained, so the network is only trained long enough to create its layers."""
-    import math
+def posterior_ic_marsaglia_workload(dev, budget_s=5.0):
+    """BASELINE configs[2]: GaussianUnknownMeanMarsaglia (stochastic control flow), IC posterior, 64k particles through
+    Model.posterior_results (lock-step while_loop; LSTM h=512).  Throughput does not depend on how well the proposals are
+    trained, so the network is only trained long enough to create its layers."""
+    import contextlib
+    import io
+    import re
     import pyprob_b200 as pyprob
+    from oracle import posterior as opost
     from pyprob_b200 import InferenceEngine, InferenceNetwork, Model
     from pyprob_b200.distributions import Normal, Uniform
 
@@ -627,29 +736,35 @@ def ic_posterior_extra():
     pyprob.seed(3)
     pyprob.set_verbosity(0)
     m = Marsaglia()
-    import contextlib
-    import io
-    with contextlib.redirect_stdout(io.StringIO()):
+    import warnings
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter('ignore')
         m.learn_inference_network(num_traces=20 * 1024, batch_size=1024, inference_network=InferenceNetwork.LSTM,
                                   lstm_dim=512, observe_embeddings={'obs0': {'dim': 32}, 'obs1': {'dim': 32}})
-    n = 65536
-    m.posterior_results(n, InferenceEngine.IMPORTANCE_SAMPLING_WITH_INFERENCE_NETWORK, observe={'obs0': 8, 'obs1': 9})
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    reps = 3
-    for _ in range(reps):
-        post = m.posterior_results(n, InferenceEngine.IMPORTANCE_SAMPLING_WITH_INFERENCE_NETWORK,
-                                   observe={'obs0': 8, 'obs1': 9})
-        _ = post.effective_sample_size
-    torch.cuda.synchronize()
-    return {'ic_posterior_marsaglia_particles_per_sec_n65536': reps * n / (time.perf_counter() - t0),
-            'ic_posterior_marsaglia_addresses': len(m._inference_network._addresses)}
+        value, ess = _time_posterior(m, 65536, InferenceEngine.IMPORTANCE_SAMPLING_WITH_INFERENCE_NETWORK, 3)
+    net = m._inference_network
+    P = {k: v.cpu() for k, v in net.reference_state_dict().items()}
+    table = {}
+    for a in net._addresses:
+        mt = re.search(r'__([xy])__Uniform__(\d+)$', a)
+        if mt:
+            table[(mt.group(1), int(mt.group(2)))] = a
+    torch.set_num_threads(1)
+    done, spent = _timed_cpu(lambda n: opost.marsaglia_ic(n, P, lambda var, k: table.get((var, k))), 50, budget_s)
+    cb = _cpu_entry(done, spent, 'rejection loop, per site one LSTM step (h=512) + truncated-normal-mixture proposal '
+                                 'draw + log p - log q')
+    return {'metric': 'ic_posterior_particles_per_sec', 'value': value, 'unit': 'particles/s', 'particles': 65536,
+            'ess': ess, 'addresses': len(net._addresses), 'cpu_baseline': cb, 'ratio_to_cpu_baseline': value / cb['value'],
+            'config': 'GaussianUnknownMeanMarsaglia, LSTM h=512 (same weights on both sides), 64k particles (BASELINE configs[2])'}
 
 
-def synthetic50_extra(dev, B=512, T=50):
-    """BASELINE configs[3] shape on one GPU: 50-address Normal/Categorical(4) model, LSTM h=512, obs dim 256,
-    512 traces per GPU (the per-GPU share of the 4096-trace global batch on 8 GPUs): device-resident train step."""
+def synthetic50_workload(dev, peaks, B=512, T=50, cpu_budget_s=8.0):
+    """BASELINE configs[3] shape on one GPU: 50-address Normal/Categorical(4) model, LSTM h=512, observe FF dim 256, 512 traces
+    per GPU (the per-GPU share of the 4096-trace global batch on 8 GPUs): device-resident training step, the roofline of
+    its LSTM gate-GEMM class (recurrent GEMMs forward, their dX and dW backward, P_obs), and the oracle port on the CPU."""
     import ctypes as C
+    from oracle import network as onet
+    from oracle import params as oparams
     from pyprob_b200 import synthetic
     from pyprob_b200._lib import call, ptr
     from pyprob_b200.network import BatchStruct
@@ -659,7 +774,8 @@ def synthetic50_extra(dev, B=512, T=50):
     net._optimizer_type, net._learning_rate_init, net._weight_decay = Optimizer.ADAM, 1e-3, 0.0
     net._create_optimizer()
     net._sync_native()
-    enc = synthetic.synthetic50_batch(rng, B, T=T).encode(net)
+    batch = synthetic.synthetic50_batch(rng, B, T=T)
+    enc = batch.encode(net)
     grad = torch.zeros_like(net._arena.data)
     img = torch.from_numpy(enc.pack().copy()).pin_memory()
     dimg = img.to(dev)
@@ -683,16 +799,60 @@ def synthetic50_extra(dev, B=512, T=50):
     for _ in range(3):
         step()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
     reps = 10
-    for _ in range(reps):
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in evs:
+        a.record()
         step()
-    e1.record()
+        b.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    return {'synthetic50_train_traces_per_sec_b512': B / (ms * 1e-3), 'synthetic50_ms_per_step_b512': ms,
-            'synthetic50_parameters': int(net._arena.numel())}
+    ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    # roofline of the gate-GEMM class: per-launch CUDA events inside the step
+    call('ppb_prof_enable', 1)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    pms, pn, pfl = C.c_double(), C.c_int64(), C.c_double()
+    call('ppb_prof_read', C.byref(pms), C.byref(pn), C.byref(pfl))
+    call('ppb_prof_enable', 0)
+    tf32_peak = peaks['bf16_tflops_sustained'] / 2.0     # kernels timed inside a multi-millisecond step
+    achieved = pfl.value / (pms.value * 1e-3) / 1e12 if pms.value > 0 else 0.0
+    roof = {'bound': 'tensor', 'kernel': 'LSTM gate GEMM class at T=50 (recurrent h W_hh^T per step, BPTT dX, dW_hh, P_obs)',
+            'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': achieved / tf32_peak,
+            'frac_issued_mma': 3.0 * achieved / tf32_peak, 'traffic': committed_traffic('gate_gemm_synthetic50'),
+            'launches_per_step': pn.value / 3, 'gate_gemm_ms_per_step': pms.value / 3,
+            'flops_per_step': pfl.value / 3,
+            'peak_source': '{} bf16_tflops_sustained / 2 = tf32 dense'.format(peaks['source'])}
+    # CPU: the oracle port on minibatches of the same model (256 traces per step keeps the sample bounded)
+    Bc = 256
+    P = oparams.random_params([('obs', 1, 256, 2)], synthetic.synthetic50_addresses(T), lstm_dim=512, K=10, seed=0)
+    plist = {k: v.requires_grad_(True) for k, v in P.items()}
+    opt = torch.optim.Adam(list(plist.values()), lr=1e-3)
+    sb = synthetic.synthetic50_batch(np.random.default_rng(6), Bc, T=T).subs
+    subs = [{k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in x.items()} for x in sb]
+    torch.set_num_threads(os.cpu_count() or 1)
+
+    def cpu_step():
+        opt.zero_grad()
+        l, _ = onet.loss(plist, subs, ['obs'], [1], 10)
+        l.backward()
+        opt.step()
+    cpu_step()
+    t0 = time.perf_counter()
+    done = 0
+    while done < 1 or time.perf_counter() - t0 < cpu_budget_s:
+        cpu_step()
+        done += 1
+    dt = time.perf_counter() - t0
+    cb = {'value': done * Bc / dt, 'unit': 'traces/s', 'cores': os.cpu_count(), 'kind': 'port',
+          'sample': '{} steps of _loss+backward+Adam on {}-trace minibatches of the 50-address model (oracle/network.py, torch '
+                    'CPU fp32, all host threads), {:.1f} s'.format(done, Bc, dt)}
+    value = B / (ms * 1e-3)
+    return {'metric': 'ic_train_traces_per_sec', 'value': value, 'unit': 'traces/s', 'ms_per_step': ms, 'batch': B,
+            'trace_length': T, 'parameters': int(net.num_parameters()), 'roofline': roof, 'cpu_baseline': cb,
+            'ratio_to_cpu_baseline': value / cb['value'],
+            'config': 'synthetic 50-address Normal/Categorical(4) model, T=50, observe FF dim 256 depth 2, LSTM h=512, '
+                      '512 traces (per-GPU share of BASELINE configs[3]), device-resident step, back to back'}
 
 
 if __name__ == '__main__':

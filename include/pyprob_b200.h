@@ -289,7 +289,8 @@ int ppb_adam_step(float* arena, const float* grad, float* exp_avg, float* exp_av
 /* Same update with the step counter and hyper-parameters in device memory, so that a whole training step
  * (forward, backward, optimiser) can be captured once in a CUDA graph and replayed.
  *   hyper_dev: float[6] = lr, beta1, beta2, eps, weight_decay, grad_scale
- *   state_dev: 16 bytes: int64 step counter (incremented by the call), float bc1, float sqrt(bc2) */
+ *   state_dev: 16 bytes, zero-initialised: int64 step counter (incremented by the call), float bc1 of the last step,
+ *              uint32 scratch (finished-block count, zero between calls) */
 int ppb_adam_step_dev(float* arena, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                       const float* hyper_dev, void* state_dev, void* stream);
 
@@ -333,6 +334,11 @@ int ppb_dp_alloc(int64_t bytes, void** ptr_out, void* ipc_handle_out /* 64 bytes
 int ppb_dp_open(const void* ipc_handle /* 64 bytes, from another process */, void** ptr_out);
 int ppb_dp_close(void* mapped_ptr);
 int ppb_dp_free(void* ptr);
+/* Stream-ordered cross-rank rendezvous over the same peer blocks (one tiny kernel: each rank releases a flag word in
+ * every peer's block and waits for all of its own): work enqueued after it starts on all ranks at the same time.
+ * Replaces the host-side dist.barrier() of the reference's training loop where only stream order matters; bench.py
+ * uses it to start every timed step simultaneously on all ranks (the L2 flush before it is not part of the step). */
+int ppb_dp_rendezvous(int world, int rank, void* const* peer_blocks, int64_t flag_off, void* stream);
 int ppb_dp_adam_step(int world, int rank, void* const* peer_blocks /* host array [world], own block at [rank] */,
                      int64_t param_off, int64_t grad_off, int64_t flag_off, float* exp_avg,
                      float* exp_avg_sq, int64_t n, int64_t n_extra, const float* hyper_dev, void* state_dev,
@@ -385,6 +391,13 @@ int ppb_pack_tf32_mn(const float* X, int64_t rows, int64_t K, int64_t ldx, float
 int ppb_gemm_packed(const float* A_hi, const float* A_lo, const float* B_hi, const float* B_lo,
                     float* C, int64_t M, int64_t N, int64_t K, int64_t ldc, const float* bias,
                     int relu, int precision, void* stream);
+/* Same GEMM with the reduction of every 128 x 128 output tile split over a thread-block cluster of cluster_size (2, 4, 8)
+ * CTAs whose partial tiles are combined through distributed shared memory (csrc/tc_cluster.cuh): the form the network
+ * uses for its few-row, deep-K GEMMs — nn.LSTM's recurrent product h W_hh^T and its BPTT mirror
+ * (pyprob/nn/inference_network_lstm.py:186-188), the proposal heads at small minibatches. */
+int ppb_gemm_packed_cluster(const float* A_hi, const float* A_lo, const float* B_hi, const float* B_lo,
+                            float* C, int64_t M, int64_t N, int64_t K, int64_t ldc, const float* bias,
+                            int relu, int precision, int cluster_size, void* stream);
 
 /* Phase-trace buffer for the tensor-core grouped GEMM: 64 launches x 16 int64 slots of globaltimer stamps written by
  * CTA 0 of each launch (setup, first data, last MMA commit, accumulators ready, epilogue done); NULL disables. */

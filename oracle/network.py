@@ -126,8 +126,17 @@ def sample_embedding(params, address, family, num_categories, values):
     return _ff(x, params, '_layers_sample_embedding.{}'.format(address), True)
 
 
-def loss(params, sub_batches, observe_names, observe_in_dims, K, sample_dim=4, addr_dim=64, type_dim=8):
-    """-> (loss, per-sub-batch list of [T,B] log-prob tensors).  sub_batches: dicts from sub_batch_from_traces."""
+def loss(params, sub_batches, observe_names, observe_in_dims, K, sample_dim=4, addr_dim=64, type_dim=8,
+         repaired_rows='reference'):
+    """-> (loss, per-sub-batch list of [T,B] log-prob tensors).  sub_batches: dicts from sub_batch_from_traces.
+
+    repaired_rows: what happens to the GRADIENT of rows whose log q is -inf and gets replaced by log(1e-8)
+    (inference_network_lstm.py:207-217, util.py:278-284).  The VALUE is the same either way.
+      'reference'  the reference's own autograd graph: the replaced entries receive a zero upstream gradient, but the
+                   backward of logsumexp multiplies it by softmax(-inf, ..., -inf) = NaN, so EVERY shared parameter gets
+                   a NaN gradient (and the reference's next optimizer.step() destroys the network) — kept to document it;
+      'constant'   the replaced value is the constant the reference's code intends: such rows contribute no gradient
+                   (the head is evaluated on the remaining rows only).  This is what the CUDA path implements."""
     total = 0.0
     batch_size = sum(sb['values'].size(1) for sb in sub_batches)
     all_lp = []
@@ -155,17 +164,26 @@ def loss(params, sub_batches, observe_names, observe_in_dims, K, sample_dim=4, a
             lp = head_log_prob(params, sb['addresses'][t], sb['families'][t], sb['num_categories'][t], K, out[t],
                                sb['values'][t], sb['prior0'][t], sb['prior1'][t])
             if torch.isinf(lp).any() and not torch.isnan(lp).any():
-                lp = lp.clone()
-                lp[lp == -float('inf')] = LOG_EPSILON   # util.replace_negative_inf: constant, no gradient
+                dead = lp == -float('inf')
+                if repaired_rows == 'constant' and bool(dead.any()) and not bool(dead.all()):
+                    keep = torch.nonzero(~dead).view(-1)
+                    live = head_log_prob(params, sb['addresses'][t], sb['families'][t], sb['num_categories'][t], K,
+                                         out[t][keep], sb['values'][t][keep], sb['prior0'][t][keep], sb['prior1'][t][keep])
+                    lp = torch.full_like(lp, LOG_EPSILON).index_copy(0, keep, live)
+                else:
+                    lp = lp.clone()
+                    lp[dead] = LOG_EPSILON   # util.replace_negative_inf
+                    if repaired_rows == 'constant':
+                        lp = lp.detach()
             lps.append(lp)
             total = total + (-lp.sum())
         all_lp.append(torch.stack(lps))
     return total / batch_size, all_lp
 
 
-def loss_and_grads(params, sub_batches, observe_names, observe_in_dims, K):
+def loss_and_grads(params, sub_batches, observe_names, observe_in_dims, K, repaired_rows='reference'):
     p = {k: v.clone().float().requires_grad_(True) for k, v in params.items()}
-    value, lps = loss(p, sub_batches, observe_names, observe_in_dims, K)
+    value, lps = loss(p, sub_batches, observe_names, observe_in_dims, K, repaired_rows=repaired_rows)
     value.backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in p.items()}
     return value.detach(), grads, [x.detach() for x in lps]

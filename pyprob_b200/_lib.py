@@ -62,6 +62,7 @@ _SIGNATURES = {
     'ppb_dp_open': [C.c_void_p, C.c_void_p],
     'ppb_dp_close': [c_f],
     'ppb_dp_free': [c_f],
+    'ppb_dp_rendezvous': [c_int, c_int, C.c_void_p, c_i64, c_f],
     'ppb_dp_adam_step': [c_int, c_int, C.c_void_p, c_i64, c_i64, c_i64, c_f, c_f, c_i64, c_i64, c_f, c_f, c_f],
     'ppb_ic_infer_step': [C.c_void_p, c_f, c_f, c_int, c_i32, c_f, c_i32, c_f, c_int, c_f, c_int, c_f, c_f, c_f,
                           c_i64, c_f, c_i64, c_int, c_f],
@@ -76,6 +77,7 @@ _SIGNATURES = {
     'ppb_debug_trace': [c_f],
     'ppb_gemm_packed_tn': [c_f, c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_int, c_f],
     'ppb_gemm_packed': [c_f, c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_f, c_int, c_int, c_f],
+    'ppb_gemm_packed_cluster': [c_f, c_f, c_f, c_f, c_f, c_i64, c_i64, c_i64, c_i64, c_f, c_int, c_int, c_int, c_f],
 }
 _RESTYPES = {
     'ppb_ic_workspace_bytes': c_i64,

@@ -18,7 +18,10 @@ constexpr int kFlagB = 16;       // barrier-B words start here
 constexpr int kFlagEpoch = 32;   // launches completed by this rank
 constexpr int kFlagDone = 33;    // blocks of the running launch that finished their slice
 constexpr int kFlagTimeout = 34; // set if a barrier wait gave up
+constexpr int kFlagRvEpoch = 35; // rendezvous launches completed by this rank (ppb_dp_rendezvous)
 constexpr int kFlagTrace = 40;   // low 32 bits of %globaltimer at: kernel start, after barrier A, slice done, after barrier B
+constexpr int kFlagAccum = 44;   // running sums (ns, low 32 bits) of the three phase durations, then the launch count
+constexpr int kFlagRv = 48;      // rendezvous words, one per peer rank (kMaxWorld of them); block needs flag_off + 256 bytes
 constexpr unsigned long long kSpinLimitNs = 4000000000ull;
 
 struct Peers {
@@ -158,18 +161,49 @@ __global__ void __launch_bounds__(256) k_dp_adam(Peers P, int world, int rank, f
     __syncthreads();
     if (threadIdx.x == 0) {
       my[kFlagTrace + 3] = (uint32_t)now_ns();
+      my[kFlagAccum + 0] += my[kFlagTrace + 1] - my[kFlagTrace + 0];
+      my[kFlagAccum + 1] += my[kFlagTrace + 2] - my[kFlagTrace + 1];
+      my[kFlagAccum + 2] += my[kFlagTrace + 3] - my[kFlagTrace + 2];
+      my[kFlagAccum + 3] += 1u;
       my[kFlagDone] = 0u;
       my[kFlagEpoch] = epoch;
       *step_ctr = *step_ctr + 1;
-      bc_out[0] = s_bc[0];
-      bc_out[1] = s_bc[1];
+      bc_out[0] = s_bc[0];   // (byte 12 of the state block is scratch of ppb_adam_step_dev: left untouched)
     }
   }
+}
+
+// cross-rank rendezvous on the stream: returns once every rank's stream has reached its matching call
+__global__ void k_dp_rendezvous(Peers P, int world, int rank) {
+  uint32_t* my = P.flags[rank];
+  __shared__ uint32_t s_epoch;
+  if (threadIdx.x == 0) s_epoch = my[kFlagRvEpoch] + 1u;
+  __syncthreads();
+  const uint32_t epoch = s_epoch;
+  if ((int)threadIdx.x < world) {
+    st_release_sys(P.flags[threadIdx.x] + kFlagRv + rank, epoch);
+    wait_flag(my + kFlagRv + threadIdx.x, epoch, my + kFlagTimeout);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) my[kFlagRvEpoch] = epoch;
 }
 
 }  // namespace
 
 extern "C" {
+
+int ppb_dp_rendezvous(int world, int rank, void* const* peer_blocks, int64_t flag_off, void* stream) {
+  PPB_CHECK_ARG(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world && peer_blocks, "bad world/rank");
+  Peers P;
+  memset(&P, 0, sizeof(P));
+  for (int r = 0; r < world; ++r) {
+    PPB_CHECK_ARG(peer_blocks[r] != nullptr, "null peer block");
+    P.flags[r] = (uint32_t*)((char*)peer_blocks[r] + flag_off);
+  }
+  k_dp_rendezvous<<<1, 32, 0, (cudaStream_t)stream>>>(P, world, rank);
+  PPB_LAUNCH_CHECK();
+  return PPB_OK;
+}
 
 int ppb_dp_alloc(int64_t bytes, void** ptr_out, void* ipc_handle_out) {
   PPB_CHECK_ARG(bytes > 0 && ptr_out && ipc_handle_out, "bad arguments");

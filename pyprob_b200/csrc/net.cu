@@ -18,6 +18,7 @@
 #include "heads.cuh"
 #include "tc_grouped.cuh"
 #include "tc_lstm.cuh"
+#include "tc_cluster.cuh"
 #include "obs_mlp.cuh"
 
 using gemm::Problem;
@@ -65,14 +66,21 @@ struct ppb_net {
   int I = 0;        // LSTM input width  E + S + 2 (td + ad)
   int dh_pad = 4;   // max head hidden width, padded to 4
   int out_pad = 4;  // max head output width, padded to 4
-  // opt-in (PPB_FUSED_CELL=1, unvalidated): LSTM cell fused into the recurrent GEMM epilogue (tc_lstm.cuh)
-  int fused_cell = 0;
+  // LSTM cell fused into the recurrent GEMM (tc_lstm.cuh, tc_cluster.cuh); PPB_FUSED_CELL selects the variant
+  int fused_cell = 3;
   float* whh_il = nullptr;          // gate-interleaved K-format image of W_hh: hi part, then lo part
   int64_t whh_il_floats = 0;        // floats per part
   void* d_lstm_steps = nullptr;     // device list of tcl::Step (level 1) or tcl::Seq + row_off (level 2)
   size_t lstm_steps_cap = 0;        // bytes
   int* d_lstm_progress = nullptr;   // level 2: arrival counters (one per 128-row tile) + error flag
   int lstm_progress_cap = 0;        // ints
+  // side streams: independent branches of the step run beside the critical path (captured into the same CUDA graph)
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t fork_ev[16] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                             nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int fork_next = 0;
+  int single_stream = 0;            // PPB_SINGLE_STREAM=1: everything on the caller's stream (A/B, debugging)
+  int pack_tiles_no_hh = 0;         // weight-image tiles without W_hh (a T = 1 step never reads it)
   // pinned staging ring for problem lists
   Problem* h_stage[2] = {nullptr, nullptr};
   cudaEvent_t ev_stage[2] = {nullptr, nullptr};
@@ -294,6 +302,26 @@ int upload_and_get(ppb_net* net, const Builder& b, Problem* dev, int64_t cap, cu
   return upload_cached(net, slot, b.probs.data(), n * sizeof(Problem), dev, st);
 }
 
+// ---- side streams -------------------------------------------------------------------------------------
+// `to` continues after everything enqueued on `from` so far (event record + wait: both are graph-capturable, the
+// side stream joins the capture and must be joined back before the capture ends).
+int stream_after(ppb_net* net, cudaStream_t from, cudaStream_t to) {
+  if (from == to) return PPB_OK;
+  cudaEvent_t& ev = net->fork_ev[net->fork_next];
+  net->fork_next = (net->fork_next + 1) & 15;
+  if (!ev) PPB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  PPB_CUDA(cudaEventRecord(ev, from));
+  PPB_CUDA(cudaStreamWaitEvent(to, ev, 0));
+  return PPB_OK;
+}
+// side stream k (or the main stream itself in single-stream mode)
+int side_stream(ppb_net* net, int k, cudaStream_t main_st, cudaStream_t* out) {
+  if (net->single_stream) { *out = main_st; return PPB_OK; }
+  if (!net->side[k]) PPB_CUDA(cudaStreamCreateWithFlags(&net->side[k], cudaStreamNonBlocking));
+  *out = net->side[k];
+  return PPB_OK;
+}
+
 // ---- optional kernel-level profiling of the LSTM gate GEMM class (bench.py roofline) ---------------
 struct Prof {
   bool on = false;
@@ -443,7 +471,8 @@ __global__ void __launch_bounds__(256) k_head_nll(const float* __restrict__ out_
                                                    const float* __restrict__ values, const float* __restrict__ prior0,
                                                    const float* __restrict__ prior1, const int* __restrict__ row_trace,
                                                    int R, int K, float inv_batch, float* __restrict__ row_lp,
-                                                   float* __restrict__ d_out, HImg dimg, float* __restrict__ loss_acc) {
+                                                   float* __restrict__ d_out, HImg dimg, float* __restrict__ loss_acc,
+                                                   float* __restrict__ loss_out, int* __restrict__ status_out) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const int img_cols = (int)dimg.kb * 32;
@@ -589,6 +618,19 @@ __global__ void __launch_bounds__(256) k_head_nll(const float* __restrict__ out_
     if (local != 0.0f) atomicAdd(loss_acc, local * inv_batch);
     if (bad) atomicAdd(reinterpret_cast<int*>(loss_acc + 1), bad);
   }
+  // the last block to finish publishes the totals (loss_acc[2] counts finished blocks; zeroed with the accumulators)
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(reinterpret_cast<unsigned int*>(loss_acc + 2), 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    if (loss_out) *loss_out = atomicAdd(loss_acc, 0.0f);
+    if (status_out) *status_out = atomicAdd(reinterpret_cast<int*>(loss_acc + 1), 0);
+  }
 }
 
 __global__ void k_publish_loss(const float* __restrict__ loss_acc, float* __restrict__ loss_out,
@@ -698,6 +740,66 @@ __global__ void __launch_bounds__(128) k_smp_bwd(const float* __restrict__ dgate
         }
       }
     }
+  }
+}
+
+// Same gradients with the atomics taken off the hot addresses: all rows of a (step, sub-batch) segment share their previous
+// address, so a block owns a slab of ONE segment, accumulates the tiny [S x smp_in] weight and [S] bias gradients of that
+// address in shared memory and issues one global atomic per entry per block (measured with the per-row atomics of k_smp_bwd
+// at T = 50, B = 512: 0.38 ms, 200 k atomics on ~500 addresses).
+__global__ void __launch_bounds__(128) k_smp_bwd_seg(const float* __restrict__ dgates, const float* __restrict__ w_smp_t,
+                                                      const float* __restrict__ smp_emb, const float* __restrict__ values,
+                                                      const int* __restrict__ step_prev, const int* __restrict__ step_row0,
+                                                      const int* __restrict__ step_nrows, const int* __restrict__ row_prev,
+                                                      const ppb_addr_desc* __restrict__ addrs, int H4, int S,
+                                                      int rows_per_block, float* __restrict__ grad) {
+  __shared__ float acc_b[8];
+  __shared__ float acc_w[8][heads::CMAX];
+  const int st = blockIdx.y;
+  const int pa = step_prev[st];
+  if (pa < 0) return;
+  const int seg0 = step_row0[st], r0 = seg0 + blockIdx.x * rows_per_block;
+  int r1 = r0 + rows_per_block;
+  if (r1 > seg0 + step_nrows[st]) r1 = seg0 + step_nrows[st];
+  if (r0 >= r1) return;
+  const ppb_addr_desc a = addrs[pa];
+  const bool is_cat = a.family == PPB_FAMILY_CATEGORICAL;
+  const int width = is_cat ? a.smp_in : 1;
+  for (int i = threadIdx.x; i < 8 * heads::CMAX; i += blockDim.x) (&acc_w[0][0])[i] = 0.0f;
+  if (threadIdx.x < 8) acc_b[threadIdx.x] = 0.0f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int row = r0 + warp; row < r1; row += 4) {
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.0f;
+    for (int col = lane; col < H4; col += 32) {
+      const float d = dgates[(int64_t)row * H4 + col];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < S) s[j] = fmaf(d, __ldg(w_smp_t + (int64_t)j * H4 + col), s[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < S) s[j] = ppb_warp_sum(s[j]);
+    if (lane == 0) {
+      const float x = values[row_prev[row]];
+      const int cidx = (int)x;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < S && smp_emb[(int64_t)row * S + j] > 0.0f && s[j] != 0.0f) {
+          atomicAdd(&acc_b[j], s[j]);
+          if (is_cat) { if (cidx >= 0 && cidx < a.smp_in) atomicAdd(&acc_w[j][cidx], s[j]); }
+          else atomicAdd(&acc_w[j][0], s[j] * x);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < S * (width + 1); i += blockDim.x) {
+    const int j = i / (width + 1), c = i % (width + 1);
+    if (c == width) { if (acc_b[j] != 0.0f) atomicAdd(grad + a.smp_b_off + j, acc_b[j]); }
+    else if (acc_w[j][c] != 0.0f) atomicAdd(grad + a.smp_w_off + (int64_t)j * a.smp_in + c, acc_w[j][c]);
   }
 }
 
@@ -816,7 +918,15 @@ int ppb_net_create(ppb_net** out, const ppb_net_desc* d) {
   n->desc = *d;
   n->I = d->obs_dim + d->sample_dim + 2 * (d->type_dim + d->addr_dim);
   const char* fc = getenv("PPB_FUSED_CELL");
-  n->fused_cell = (fc && (fc[0] == '1' || fc[0] == '2')) ? fc[0] - '0' : 0;   // 1: per-step launches, 2: persistent
+  // LSTM steps t >= 1: 3 (default) = recurrent GEMM + cell in one kernel per step, cluster split-K when the step has few
+  // tiles (tc_cluster.cuh); 1 = same without clusters; 2 = one persistent launch for all steps; 0 = GEMM and cell kernels
+  n->fused_cell = (fc && fc[0] >= '0' && fc[0] <= '3') ? fc[0] - '0' : 3;
+  const char* ss = getenv("PPB_SINGLE_STREAM");
+  n->single_stream = (ss && ss[0] == '1') ? 1 : 0;
+  // created up front: a training step must be capturable in a CUDA graph right after its first eager run
+  for (int i = 0; i < 16; ++i) PPB_CUDA(cudaEventCreateWithFlags(&n->fork_ev[i], cudaEventDisableTiming));
+  if (!n->single_stream)
+    for (int i = 0; i < 2; ++i) PPB_CUDA(cudaStreamCreateWithFlags(&n->side[i], cudaStreamNonBlocking));
   *out = n;
   return PPB_OK;
 }
@@ -857,6 +967,8 @@ int ppb_net_destroy(ppb_net* net) {
     if (net->h_blob[i]) cudaFreeHost(net->h_blob[i]);
     if (net->ev_blob[i]) cudaEventDestroy(net->ev_blob[i]);
   }
+  for (int i = 0; i < 2; ++i) if (net->side[i]) cudaStreamDestroy(net->side[i]);
+  for (int i = 0; i < 16; ++i) if (net->fork_ev[i]) cudaEventDestroy(net->fork_ev[i]);
   if (net->wimg) cudaFree(net->wimg);
   if (net->d_pack) cudaFree(net->d_pack);
   if (net->whh_il) cudaFree(net->whh_il);
@@ -957,9 +1069,7 @@ int ppb_ic_loss_forward(ppb_net* net, const float* arena, const ppb_batch* b, vo
   k_head_nll<<<ew_grid((int64_t)d.R * 32, 256), 256, 0, st>>>(w.out_raw, net->out_pad, net->d_addrs, b->row_step, b->step_addr,
                                                 b->values, b->prior0, b->prior1, b->row_trace, d.R, D.mixture_k,
                                                 1.0f / (float)d.B, row_lp_out ? row_lp_out : w.row_lp,
-                                                want_grad ? w.d_out : nullptr, HImg(), w.loss_acc);
-  PPB_LAUNCH_CHECK();
-  k_publish_loss<<<1, 32, 0, st>>>(w.loss_acc, loss_out, status_out);
+                                                want_grad ? w.d_out : nullptr, HImg(), w.loss_acc, loss_out, status_out);
   PPB_LAUNCH_CHECK();
   return PPB_OK;
 }
@@ -1183,23 +1293,50 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
   }
 }
 
-__global__ void k_adam_tick(const float* __restrict__ hyper, long long* __restrict__ step, float* __restrict__ bc) {
-  if (threadIdx.x == 0) {
-    long long t = *step + 1;
-    *step = t;
-    bc[0] = (float)(1.0 - pow((double)hyper[1], (double)t));
-    bc[1] = (float)sqrt(1.0 - pow((double)hyper[2], (double)t));
-  }
-}
+// Graph-replayable Adam: step counter and hyper-parameters live in device memory.  Every block derives the bias
+// corrections of step t+1 itself; the last block to finish advances the counter (state: int64 step | float bc1 |
+// uint32 finished-block count, zero between launches).
 __global__ void __launch_bounds__(256) k_adam_dev(float* __restrict__ p, const float* __restrict__ g,
-                                                   float* __restrict__ m, float* __restrict__ v, int64_t n,
-                                                   const float* __restrict__ hyper, const float* __restrict__ bc) {
+                                                   float* __restrict__ m, float* __restrict__ v, int64_t n, int vec,
+                                                   const float* __restrict__ hyper, long long* __restrict__ step_ctr,
+                                                   float* __restrict__ bc1_out, unsigned int* __restrict__ done_ctr) {
+  __shared__ float s_bc[2];
+  __shared__ long long s_t;
+  if (threadIdx.x == 0) {
+    long long t = *step_ctr + 1;
+    s_t = t;
+    s_bc[0] = (float)(1.0 - pow((double)hyper[1], (double)t));
+    s_bc[1] = (float)sqrt(1.0 - pow((double)hyper[2], (double)t));
+  }
+  __syncthreads();
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], gscale = hyper[5];
-  const float step = lr / bc[0], bc2_sqrt = bc[1];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  const float step = lr / s_bc[0], bc2_sqrt = s_bc[1];
+  const int64_t n4 = vec ? (n >> 2) : 0;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[q], gg = reinterpret_cast<const float4*>(g)[q];
+    float4 mm = reinterpret_cast<float4*>(m)[q], vv = reinterpret_cast<float4*>(v)[q];
+    ppb_adam_update(pp.x, gg.x, mm.x, vv.x, b1, b2, eps, wd, gscale, step, bc2_sqrt);
+    ppb_adam_update(pp.y, gg.y, mm.y, vv.y, b1, b2, eps, wd, gscale, step, bc2_sqrt);
+    ppb_adam_update(pp.z, gg.z, mm.z, vv.z, b1, b2, eps, wd, gscale, step, bc2_sqrt);
+    ppb_adam_update(pp.w, gg.w, mm.w, vv.w, b1, b2, eps, wd, gscale, step, bc2_sqrt);
+    reinterpret_cast<float4*>(p)[q] = pp;
+    reinterpret_cast<float4*>(m)[q] = mm;
+    reinterpret_cast<float4*>(v)[q] = vv;
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
     float pi = p[i], mi = m[i], vi = v[i];
     ppb_adam_update(pi, g[i], mi, vi, b1, b2, eps, wd, gscale, step, bc2_sqrt);
     m[i] = mi; v[i] = vi; p[i] = pi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(done_ctr, 1u) == gridDim.x - 1) {   // every block has read the counter by now
+      *step_ctr = s_t;
+      *bc1_out = s_bc[0];
+      *done_ctr = 0u;
+    }
   }
 }
 
@@ -1439,15 +1576,15 @@ int ppb_adam_step(float* arena, const float* grad, float* exp_avg, float* exp_av
 
 // Graph-replayable Adam: the step counter and the hyper-parameters live in device memory, so a captured
 // training step stays valid while the count advances and the learning rate follows its schedule.
-//   state_dev: int64 step counter at [0], then float bias corrections at byte offset 8 (bc1, sqrt(bc2))
+//   state_dev: 16 bytes: int64 step counter at [0], float bc1 of the last step at byte 8, uint32 scratch at byte 12 (zero)
 //   hyper_dev: float[6] = lr, beta1, beta2, eps, weight_decay, grad_scale
 int ppb_adam_step_dev(float* arena, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                       const float* hyper_dev, void* state_dev, void* stream) {
   PPB_CHECK_ARG(arena && grad && exp_avg && exp_avg_sq && hyper_dev && state_dev && n > 0, "bad arguments");
-  k_adam_tick<<<1, 32, 0, (cudaStream_t)stream>>>(hyper_dev, (long long*)state_dev, (float*)((char*)state_dev + 8));
-  PPB_LAUNCH_CHECK();
-  k_adam_dev<<<ppb_grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(arena, grad, exp_avg, exp_avg_sq, n, hyper_dev,
-                                                                       (const float*)((char*)state_dev + 8));
+  const int vec = ((((uintptr_t)arena | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0) ? 1 : 0;
+  k_adam_dev<<<ppb_grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(
+      arena, grad, exp_avg, exp_avg_sq, n, vec, hyper_dev, (long long*)state_dev, (float*)((char*)state_dev + 8),
+      (unsigned int*)((char*)state_dev + 12));
   PPB_LAUNCH_CHECK();
   return PPB_OK;
 }

@@ -1,0 +1,357 @@
+// Cluster split-K tcgen05 GEMM: small-M problems spread over the SMs without atomics.
+//
+// The proposal network's per-time-step GEMMs have few rows (one minibatch: M = 256 .. 512) and a deep reduction
+// (K = 512 forward, K = 2048 in BPTT).  One 128 x 128 tile per CTA leaves most SMs idle and makes one CTA walk the whole
+// reduction at the per-SM operand-ingest rate (measured ~100 GB/s: 0.64 us per 32-element chunk in 3xTF32); global
+// split-K (tc_grouped.cuh) fixes the parallelism but pays one fp32 red.add per element per split (measured 33 us for the
+// 512 x 512 x 2048 BPTT GEMM, 9.4 MB of atomics).  Here the CS splits of one output tile form a thread-block CLUSTER:
+// every CTA accumulates its K-slice in TMEM, parks the fp32 partial tile in its own shared memory (the operand stages
+// are idle by then), and after a cluster barrier each CTA reduces 128 / CS rows of the tile over all partials through
+// distributed shared memory (ld.shared::cluster) and runs the epilogue for those rows only.  No atomics, no zero-fill,
+// fixed summation order, and the epilogue work is spread over the cluster too.
+//
+// Epilogues (reduce phase; one thread owns one row x four columns {lane, lane+32, lane+64, lane+96} of the tile):
+//   k_cluster<X3, CS, 0>   fp32 store (+bias, ReLU, zero-invalid rows)           BPTT dX, head dX
+//   k_cluster<X3, CS, 2>   tile images (+fp32, ReLU-mask from an image)          head hidden layer and its gradient
+//   k_lstm_cluster<X3, CS> LSTM cell: with gate-interleaved W_hh the four columns of a thread are the gates i, f, g, o
+//                          of ONE hidden unit, so the cell update is thread-local (tc_lstm.cuh has the layout)
+// Mainloop, descriptors, the three-accumulator 3xTF32 scheme: tc_grouped.cuh.
+#pragma once
+#include "tc_grouped.cuh"
+#include "tc_lstm.cuh"
+
+namespace tcc {
+
+using namespace tc;
+
+constexpr int kPitch = 129;                  // floats per row of the parked partial tile: bank = (row + col) mod 32
+constexpr int kPartFloats = 128 * kPitch;    // 66 KB, aliases the operand stages
+static_assert(kPartFloats * 4 <= 2 * tcg::kStages * kTileBytes, "partial tile must fit in the A stages");
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {   // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_smem_addr), "r"(rank));
+  return ra;
+}
+__device__ __forceinline__ float ld_cluster(uint32_t cluster_addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+  return v;
+}
+
+struct __align__(1024) Smem {
+  float a_hi[tcg::kStages][kTileFloats];
+  float a_lo[tcg::kStages][kTileFloats];
+  float b_hi[tcg::kStages][kTileFloats];
+  float b_lo[tcg::kStages][kTileFloats];
+  uint64_t full[tcg::kStages];
+  uint64_t empty[tcg::kStages];
+  uint64_t tmem_full;
+  uint32_t tmem_base;
+  union { tcg::Problem prob; tcl::Step step; };
+};
+inline size_t smem_bytes() { return sizeof(Smem) + 1024; }
+
+// Mainloop over this CTA's K-slice [c0, c1) of output tile (mt, nt), then the partial tile parked in shared memory.
+// Called by all threads; returns after the first cluster barrier (every partial of the cluster is readable).
+template <bool X3>
+__device__ __forceinline__ void mainloop_and_park(Smem& sm, const tcg::Operand& A, const tcg::Operand& B, int mt, int nt,
+                                                  int c0, int c1, uint32_t tmem, int warp, int lane) {
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t bytes = (tcg::stage_bytes(A, mt) + tcg::stage_bytes(B, nt)) * (X3 ? 2u : 1u);
+      for (int c = c0; c < c1; ++c) {
+        int s = (c - c0) % tcg::kStages;
+        uint32_t ph = ((c - c0) / tcg::kStages) & 1;
+        mbar_wait(&sm.empty[s], ph ^ 1);
+        mbar_expect_tx(&sm.full[s], bytes);
+        tcg::load_operand(A, mt, c, sm.a_hi[s], sm.a_lo[s], X3, &sm.full[s]);
+        tcg::load_operand(B, nt, c, sm.b_hi[s], sm.b_lo[s], X3, &sm.full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(128, tcg::kBN, A.mn, B.mn);
+      const bool amn = A.mn != 0, bmn = B.mn != 0;
+      for (int c = c0; c < c1; ++c) {
+        int s = (c - c0) % tcg::kStages;
+        uint32_t ph = ((c - c0) / tcg::kStages) & 1;
+        mbar_wait(&sm.full[s], ph);
+        fence_after_sync();
+        uint32_t sa_hi = smem_u32(sm.a_hi[s]), sa_lo = smem_u32(sm.a_lo[s]);
+        uint32_t sb_hi = smem_u32(sm.b_hi[s]), sb_lo = smem_u32(sm.b_lo[s]);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint64_t ah = tcg::operand_desc(amn, sa_hi, ks), bh = tcg::operand_desc(bmn, sb_hi, ks);
+          if (X3) {
+            uint64_t al = tcg::operand_desc(amn, sa_lo, ks), bl = tcg::operand_desc(bmn, sb_lo, ks);
+            mma_tf32(tmem + 2 * tcg::kBN, al, bh, idesc, (c == c0 && ks == 0) ? 0u : 1u);
+            mma_tf32(tmem + 2 * tcg::kBN, ah, bl, idesc, 1u);
+            mma_tf32(tmem + (c & 1) * tcg::kBN, ah, bh, idesc, (c - c0 < 2 && ks == 0) ? 0u : 1u);
+          } else {
+            mma_tf32(tmem, ah, bh, idesc, (c == c0 && ks == 0) ? 0u : 1u);
+          }
+        }
+        mma_commit(&sm.empty[s]);
+      }
+      mma_commit(&sm.tmem_full);
+    }
+  } else {
+    // thread = TMEM lane = row of the tile; 32 consecutive columns per load
+    const int q = warp & 3, cb = (warp - 2) >> 2;
+    float* part = reinterpret_cast<float*>(sm.a_hi);
+    mbar_wait(&sm.tmem_full, 0);
+    fence_after_sync();
+    float v[32];
+    if (c1 > c0) {
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (X3 ? (c0 & 1) * tcg::kBN : 0) + cb * 32, v);
+      if (X3) {
+        float u[32];
+        if (c1 - c0 > 1) {
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ((c0 & 1) ^ 1) * tcg::kBN + cb * 32, u);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += u[j];
+        }
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 2 * tcg::kBN + cb * 32, u);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += u[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+    }
+    float* dst = part + (q * 32 + lane) * kPitch + cb * 32;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) dst[j] = v[j];
+  }
+  fence_before_sync();
+  cluster_sync_all();
+  fence_after_sync();
+}
+
+// sum of the CS partials at (row, lane + 32 g), g = 0..3, in fixed split order
+template <int CS>
+__device__ __forceinline__ void reduce_row(const Smem& sm, int row, int lane, float (&v)[4]) {
+  const uint32_t local = smem_u32(reinterpret_cast<const float*>(sm.a_hi) + row * kPitch + lane);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) v[g] = 0.0f;
+#pragma unroll
+  for (int s = 0; s < CS; ++s) {
+    const uint32_t base = map_to_rank(local, (uint32_t)s);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) v[g] += ld_cluster(base + g * 32 * 4);
+  }
+}
+
+__device__ __forceinline__ void common_setup(Smem& sm, int warp, int lane) {
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < tcg::kStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+    mbar_init(&sm.tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<tcg::kTmemCols>(&sm.tmem_base);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+}
+
+// ---- generic flavours -------------------------------------------------------------------------------------------------
+// grid = (sum of tiles) * CS, cluster (CS, 1, 1): blockIdx.x / CS = tile, %cluster_ctarank = K-split.
+template <bool X3, int CS, int EPI>
+__global__ void __launch_bounds__(tcg::kThreads, 1) k_cluster(const tcg::Problem* __restrict__ probs, int n_probs) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x / CS;
+  const int split = (int)cluster_ctarank();
+  int lo_i = 0, hi_i = n_probs - 1;
+  while (lo_i < hi_i) {
+    int mid = (lo_i + hi_i + 1) >> 1;
+    if (probs[mid].tile_start <= tile) lo_i = mid; else hi_i = mid - 1;
+  }
+  for (int i = threadIdx.x; i < (int)(sizeof(tcg::Problem) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(&sm.prob)[i] = reinterpret_cast<const uint32_t*>(probs + lo_i)[i];
+  __syncthreads();
+  const tcg::Problem& P = sm.prob;
+  const int local = tile - P.tile_start;
+  const int mt = local / P.tiles_n, nt = local % P.tiles_n;
+  const int KC = (P.K + 31) / 32;
+  const int c0 = (int)((int64_t)KC * split / CS), c1 = (int)((int64_t)KC * (split + 1) / CS);
+  common_setup(sm, warp, lane);
+  const uint32_t tmem = sm.tmem_base;
+  mainloop_and_park<X3>(sm, P.a, P.b, mt, nt, c0, c1, tmem, warp, lane);
+
+  if (warp >= 2) {
+    constexpr int kRowsPerCta = 128 / CS, kRowsPerWarp = kRowsPerCta / tcg::kEpiWarps;
+    const int ew = warp - 2;
+    const bool do_relu = (P.flags & tcg::kRelu) != 0, do_mask = (P.flags & tcg::kMaskImg) != 0;
+    const int m_valid = (P.flags & tcg::kZeroInvalid) ? P.m_valid : P.M;
+    float bias[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int n = nt * 128 + g * 32 + lane;
+      bias[g] = (P.bias && n < P.N) ? __ldg(P.bias + n) : 0.0f;
+    }
+#pragma unroll
+    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+      const int row = split * kRowsPerCta + ew * kRowsPerWarp + rr;   // row of the tile
+      const int m = mt * 128 + row;
+      if (m >= P.M) continue;   // warp-uniform
+      float v[4];
+      reduce_row<CS>(sm, row, lane, v);
+      const int64_t orow = (int64_t)P.o_row0 + m;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int n = nt * 128 + g * 32 + lane;
+        if (g * 32 >= ((P.N - nt * 128 + 31) & ~31)) continue;   // warp-uniform: column block beyond the (padded) width
+        float x = v[g] + bias[g];
+        x = do_relu ? fmaxf(x, 0.0f) : x;
+        x = (n < P.N && m < m_valid) ? x : 0.0f;
+        if (EPI == 0) {
+          if (P.c && n < P.N) tcg::st_global(P.c + (int64_t)m * P.ldc + n, x);
+        } else {
+          const int64_t ocb = P.o_col0 / 32 + nt * 4 + g;
+          const int64_t span = ((orow >> 7) * P.o_kb + ocb) * kTileFloats + (orow & 127) * 32;
+          const int64_t pos_k = span + ((((lane >> 2) ^ (int)(orow & 7))) << 2) + (lane & 3);
+          if (do_mask) x = (tcg::ld_global(P.mask_hi + pos_k) > 0.0f) ? x : 0.0f;
+          if (P.c && n < P.N) tcg::st_global(P.c + (int64_t)m * P.ldc + n, x);
+          float h, l;
+          split_tf32(x, h, l);
+          if (P.o_k_hi) { tcg::st_global(P.o_k_hi + pos_k, h); tcg::st_global(P.o_k_lo + pos_k, l); }
+          if (P.o_mn_hi) {
+            const int64_t pos_mn = span + ((((lane >> 3) ^ (int)(orow & 3))) << 3) + (lane & 7);
+            tcg::st_global(P.o_mn_hi + pos_mn, h);
+            tcg::st_global(P.o_mn_lo + pos_mn, l);
+          }
+        }
+      }
+    }
+  }
+  // nobody leaves (and frees its shared memory) while a peer may still be reading its partial
+  fence_before_sync();
+  cluster_sync_all();
+  if (warp == 1) {
+    fence_after_sync();
+    tmem_dealloc<tcg::kTmemCols>(tmem);
+  }
+}
+
+// ---- LSTM time step: recurrent GEMM + cell in the reduce phase --------------------------------------------------------------
+// Step list and CellIO as in tc_lstm.cuh (gate-interleaved W_hh: tile column g * 32 + j = gate g of unit nt * 32 + j).
+template <bool X3, int CS>
+__global__ void __launch_bounds__(tcg::kThreads, 1) k_lstm_cluster(const tcl::Step* __restrict__ steps, int n_steps) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x / CS;
+  const int split = (int)cluster_ctarank();
+  int lo_i = 0, hi_i = n_steps - 1;
+  while (lo_i < hi_i) {
+    int mid = (lo_i + hi_i + 1) >> 1;
+    if (steps[mid].tile_start <= tile) lo_i = mid; else hi_i = mid - 1;
+  }
+  for (int i = threadIdx.x; i < (int)(sizeof(tcl::Step) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(&sm.step)[i] = reinterpret_cast<const uint32_t*>(steps + lo_i)[i];
+  __syncthreads();
+  const tcl::Step& P = sm.step;
+  const tcl::CellIO& io = P.io;
+  const int local = tile - P.tile_start;
+  const int mt = local / P.tiles_n, nt = local % P.tiles_n;   // nt = block of 32 hidden units
+  const int KC = (io.H + 31) / 32;
+  const int c0 = (int)((int64_t)KC * split / CS), c1 = (int)((int64_t)KC * (split + 1) / CS);
+  common_setup(sm, warp, lane);
+  const uint32_t tmem = sm.tmem_base;
+  mainloop_and_park<X3>(sm, P.a, P.b, mt, nt, c0, c1, tmem, warp, lane);
+
+  if (warp >= 2) {
+    constexpr int kRowsPerCta = 128 / CS, kRowsPerWarp = kRowsPerCta / tcg::kEpiWarps;
+    const int ew = warp - 2;
+    const int H = io.H, H4 = 4 * io.H, S = io.S;
+    const int u = nt * 32 + lane;     // hidden unit of this lane
+    float wsmp[4][8];
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int s = 0; s < 8; ++s) wsmp[g][s] = (s < S) ? __ldg(io.w_smp_t + (int64_t)s * H4 + g * H + u) : 0.0f;
+    const int64_t hkb = io.hkb;
+#pragma unroll
+    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+      const int trow = split * kRowsPerCta + ew * kRowsPerWarp + rr;
+      const int64_t row = (int64_t)P.row0 + mt * 128 + trow;     // global row of the step
+      const int tr = __ldg(io.row_trace + row);
+      float act[4] = {0.f, 0.f, 0.f, 0.f}, cn = 0.0f, hn = 0.0f;
+      if (tr >= 0) {   // warp-uniform
+        float v[4];
+        reduce_row<CS>(sm, trow, lane, v);
+        const int st = __ldg(io.row_step + row);
+        const int64_t rp = __ldg(io.row_prev + row);
+        float sm_e[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) sm_e[s] = (s < S) ? __ldg(io.smp_emb + row * S + s) : 0.0f;
+        const float cp = tcg::ld_global(io.c + rp * H + u);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int col = g * H + u;
+          // same order of additions as k_cell_fwd: (P_obs + P_step) + recurrent, then the sample-embedding FMAs
+          float x = __ldg(io.p_obs + (int64_t)tr * H4 + col) + __ldg(io.p_step + (int64_t)st * H4 + col);
+          x += v[g];
+#pragma unroll
+          for (int s = 0; s < 8; ++s)
+            if (s < S) x = fmaf(sm_e[s], wsmp[g][s], x);
+          act[g] = (g == 2) ? tanhf(x) : 1.0f / (1.0f + expf(-x));
+        }
+        cn = act[1] * cp + act[0] * act[2];
+        hn = act[3] * tanhf(cn);
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) tcg::st_global(io.gates + row * H4 + g * H + u, act[g]);
+      tcg::st_global(io.c + row * H + u, cn);
+      tcg::st_global(io.h + row * H + u, hn);
+      const int64_t span = ((row >> 7) * hkb + nt) * kTileFloats + (row & 127) * 32;
+      float hh, hl;
+      split_tf32(hn, hh, hl);
+      const int64_t pos_k = span + ((((lane >> 2) ^ (int)(row & 7))) << 2) + (lane & 3);
+      tcg::st_global(io.hk_hi + pos_k, hh);
+      tcg::st_global(io.hk_lo + pos_k, hl);
+      const int64_t pos_mn = span + ((((lane >> 3) ^ (int)(row & 3))) << 3) + (lane & 7);
+      tcg::st_global(io.hmn_hi + pos_mn, hh);
+      tcg::st_global(io.hmn_lo + pos_mn, hl);
+    }
+  }
+  fence_before_sync();
+  cluster_sync_all();
+  if (warp == 1) {
+    fence_after_sync();
+    tmem_dealloc<tcg::kTmemCols>(tmem);
+  }
+}
+
+// host-side launch with a (CS, 1, 1) cluster
+template <typename Kernel, typename... Args>
+inline cudaError_t launch_cluster(Kernel kernel, int grid, int cluster, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(tcg::kThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+}  // namespace tcc

@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "tc.cuh"
 #include "tc_grouped.cuh"
+#include "tc_cluster.cuh"
 
 namespace {
 
@@ -59,6 +60,21 @@ int launch_single(const tcg::Problem& hp, cudaStream_t st) {
   return PPB_OK;
 }
 
+template <bool X3, int CS>
+int launch_single_cluster(const tcg::Problem& hp, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    PPB_CUDA(cudaFuncSetAttribute(tcc::k_cluster<X3, CS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcc::smem_bytes()));
+    attr = true;
+  }
+  if (!g_dev_problem) PPB_CUDA(cudaMalloc((void**)&g_dev_problem, sizeof(tcg::Problem)));
+  PPB_CUDA(cudaMemcpyAsync(g_dev_problem, &hp, sizeof(hp), cudaMemcpyHostToDevice, st));
+  PPB_CUDA(tcc::launch_cluster(tcc::k_cluster<X3, CS, 0>, hp.tiles_m * hp.tiles_n * CS, CS, tcc::smem_bytes(), st,
+                               (const tcg::Problem*)g_dev_problem, 1));
+  PPB_LAUNCH_CHECK();
+  return PPB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -101,6 +117,31 @@ int ppb_gemm_packed(const float* A_hi, const float* A_lo, const float* B_hi, con
   p.c = C; p.ldc = ldc; p.bias = bias; p.flags = relu ? tcg::kRelu : 0;
   p.tiles_m = (int)((M + 127) / 128); p.tiles_n = (int)((N + 127) / 128); p.k_splits = 1;
   return precision == PPB_PREC_TF32X3 ? launch_single<true>(p, (cudaStream_t)stream) : launch_single<false>(p, (cudaStream_t)stream);
+}
+
+// Same GEMM with the reduction split over a thread-block cluster of `cluster_size` CTAs per output tile (2, 4 or 8):
+// partial tiles are combined through distributed shared memory (tc_cluster.cuh) — the kernel the network uses for its
+// few-row, deep-K GEMMs (LSTM recurrence, BPTT, proposal heads at small minibatches).
+int ppb_gemm_packed_cluster(const float* A_hi, const float* A_lo, const float* B_hi, const float* B_lo, float* C, int64_t M,
+                            int64_t N, int64_t K, int64_t ldc, const float* bias, int relu, int precision, int cluster_size,
+                            void* stream) {
+  PPB_CHECK_ARG(A_hi && B_hi && C && M > 0 && N > 0 && K > 0 && ldc >= N, "bad arguments");
+  PPB_CHECK_ARG(precision == PPB_PREC_TF32X3 || precision == PPB_PREC_TF32, "precision must be TF32X3 or TF32");
+  PPB_CHECK_ARG(precision == PPB_PREC_TF32 || (A_lo && B_lo), "3xTF32 needs the lo images");
+  PPB_CHECK_ARG(cluster_size == 2 || cluster_size == 4 || cluster_size == 8, "cluster size must be 2, 4 or 8");
+  tcg::Problem p;
+  memset(&p, 0, sizeof(p));
+  const int kb = (int)((K + 31) / 32);
+  p.a.hi = A_hi; p.a.lo = A_lo; p.a.kb = kb;
+  p.b.hi = B_hi; p.b.lo = B_lo; p.b.kb = kb;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.c = C; p.ldc = ldc; p.bias = bias; p.flags = relu ? tcg::kRelu : 0;
+  p.tiles_m = (int)((M + 127) / 128); p.tiles_n = (int)((N + 127) / 128); p.k_splits = 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool x3 = precision == PPB_PREC_TF32X3;
+  if (cluster_size == 2) return x3 ? launch_single_cluster<true, 2>(p, st) : launch_single_cluster<false, 2>(p, st);
+  if (cluster_size == 4) return x3 ? launch_single_cluster<true, 4>(p, st) : launch_single_cluster<false, 4>(p, st);
+  return x3 ? launch_single_cluster<true, 8>(p, st) : launch_single_cluster<false, 8>(p, st);
 }
 
 int ppb_gemm_packed_tn(const float* X_hi, const float* X_lo, const float* Y_hi, const float* Y_lo, float* C, int64_t M,

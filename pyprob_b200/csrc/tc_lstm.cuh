@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(tcg::kThreads, 1) k_lstm_seq(const Seq* __rest
 inline size_t smem_bytes() { return sizeof(Smem) + 1024; }
 
 // W_hh [4H, H] (row-major, gate-major rows) -> K-format hi / lo tile image with gate-interleaved rows
-__global__ void __launch_bounds__(256) k_pack_whh_interleaved(const float* __restrict__ w_hh, int H,
+static __global__ void __launch_bounds__(256) k_pack_whh_interleaved(const float* __restrict__ w_hh, int H,
                                                                float* __restrict__ img_hi, float* __restrict__ img_lo) {
   const int kb = H / 32;
   const int rt = blockIdx.x;             // packed row tile = block of 32 hidden units

@@ -94,7 +94,7 @@ class PeerAdam:
         self.param_off = 0
         self.grad_off = pad(self.n) * 4
         self.flag_off = self.grad_off + pad(self.n + self.N_EXTRA) * 4
-        nbytes = self.flag_off + 256
+        nbytes = self.flag_off + 512
         own = C.c_void_p()
         handle = C.create_string_buffer(64)
         _lib.call('ppb_dp_alloc', nbytes, C.byref(own), handle)
@@ -117,7 +117,7 @@ class PeerAdam:
         self._raw = raw
         self.params = raw[:self.n * 4].view(torch.float32)
         self.grad = raw[self.grad_off:self.grad_off + (self.n + self.N_EXTRA) * 4].view(torch.float32)
-        self._flags = raw[self.flag_off:self.flag_off + 256].view(torch.int32)
+        self._flags = raw[self.flag_off:self.flag_off + 512].view(torch.int32)
         if self.world > 1:
             dist.barrier()   # every block is mapped (and zeroed) before anyone's first step
 
@@ -128,6 +128,22 @@ class PeerAdam:
         _lib.call('ppb_dp_adam_step', self.world, self.rank, self._blocks, self.param_off, self.grad_off,
                   self.flag_off, _lib.ptr(exp_avg), _lib.ptr(exp_avg_sq), self.n, self.N_EXTRA, _lib.ptr(hyper_dev),
                   _lib.ptr(state_dev), stream)
+
+    def rendezvous(self, stream):
+        """Stream-ordered cross-rank rendezvous (ppb_dp_rendezvous): later work on `stream` starts together on all ranks."""
+        from . import _lib
+        _lib.call('ppb_dp_rendezvous', self.world, self.rank, self._blocks, self.flag_off, stream)
+
+    def phase_totals_us(self, reset=False):
+        """Mean durations (us) of the phases of ppb_dp_adam_step over the launches since the last reset: wait at barrier A
+        (cross-rank skew of the backward passes), slice (peer loads + Adam + peer stores), wait at barrier B."""
+        acc = [int(x) & 0xffffffff for x in self._flags[44:48].tolist()]
+        n = max(acc[3], 1)
+        out = {'launches': acc[3], 'barrier_a': acc[0] * 1e-3 / n, 'slice': acc[1] * 1e-3 / n,
+               'barrier_b': acc[2] * 1e-3 / n}
+        if reset:
+            self._flags[44:48].zero_()
+        return out
 
     def timed_out(self):
         """True if a cross-rank barrier gave up waiting (a rank died or fell out of step)."""

@@ -85,3 +85,26 @@ def test_gemm_packed_tn(cuda, M, N, R, precision):
     err = np.abs(got - want).max() / np.sqrt(R)
     assert np.isfinite(got).all()
     assert err < (8e-6 if precision == 0 else 3e-3), err
+
+
+@pytest.mark.parametrize('M,N,K,cs', [(128, 128, 64, 2), (512, 2048, 512, 2), (512, 512, 2048, 8), (256, 271, 512, 8),
+                                      (100, 70, 500, 4), (300, 96, 271, 4), (256, 30, 300, 2), (129, 257, 96, 2)])
+@pytest.mark.parametrize('precision', [0, 1])
+def test_gemm_packed_cluster_split_k(cuda, M, N, K, cs, precision):
+    """Cluster split-K (tc_cluster.cuh): the reduction of every output tile is divided over `cs` CTAs of one thread-block
+    cluster and the partial tiles meet in distributed shared memory — same result as the single-CTA kernel."""
+    gen = torch.Generator().manual_seed(M * 5 + N * 3 + K + cs)
+    a = torch.randn(M, K, generator=gen)
+    b = torch.randn(N, K, generator=gen)
+    bias = torch.randn(N, generator=gen)
+    want = (a.double() @ b.double().t() + bias.double()).clamp(min=0).numpy()
+    ah, al = _pack(a.to(cuda))
+    bh, bl = _pack(b.to(cuda))
+    c = torch.full((M, N), float('nan'), device=cuda)
+    call('ppb_gemm_packed_cluster', ptr(ah), ptr(al), ptr(bh), ptr(bl), ptr(c), M, N, K, N, ptr(bias.to(cuda)), 1, precision,
+         cs, stream())
+    torch.cuda.synchronize()
+    got = c.cpu().double().numpy()
+    assert np.isfinite(got).all()
+    err = np.abs(got - want).max() / np.sqrt(K)
+    assert err < (8e-6 if precision == 0 else 3e-3), err
