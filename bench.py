@@ -830,23 +830,33 @@ def synthetic50_workload(dev, peaks, B=512, T=50, cpu_budget_s=8.0):
     opt = torch.optim.Adam(list(plist.values()), lr=1e-3)
     sb = synthetic.synthetic50_batch(np.random.default_rng(6), Bc, T=T).subs
     subs = [{k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in x.items()} for x in sb]
-    torch.set_num_threads(os.cpu_count() or 1)
-
     def cpu_step():
         opt.zero_grad()
         l, _ = onet.loss(plist, subs, ['obs'], [1], 10)
         l.backward()
         opt.step()
-    cpu_step()
+    # a step is thousands of small torch ops: more threads than the GEMMs can feed only add synchronisation cost
+    ncpu = os.cpu_count() or 1
+    best = None
+    for nt in sorted(set(min(ncpu, x) for x in (8, 16, 32, 64))):
+        torch.set_num_threads(nt)
+        t0 = time.perf_counter()
+        cpu_step()
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[1]:
+            best = (nt, dt)
+        if dt > 20.0:
+            break
+    torch.set_num_threads(best[0])
     t0 = time.perf_counter()
     done = 0
     while done < 1 or time.perf_counter() - t0 < cpu_budget_s:
         cpu_step()
         done += 1
     dt = time.perf_counter() - t0
-    cb = {'value': done * Bc / dt, 'unit': 'traces/s', 'cores': os.cpu_count(), 'kind': 'port',
+    cb = {'value': done * Bc / dt, 'unit': 'traces/s', 'cores': best[0], 'kind': 'port',
           'sample': '{} steps of _loss+backward+Adam on {}-trace minibatches of the 50-address model (oracle/network.py, torch '
-                    'CPU fp32, all host threads), {:.1f} s'.format(done, Bc, dt)}
+                    'CPU fp32, {} of {} host threads — the fastest of 8/16/32/64), {:.1f} s'.format(done, Bc, best[0], ncpu, dt)}
     value = B / (ms * 1e-3)
     return {'metric': 'ic_train_traces_per_sec', 'value': value, 'unit': 'traces/s', 'ms_per_step': ms, 'batch': B,
             'trace_length': T, 'parameters': int(net.num_parameters()), 'roofline': roof, 'cpu_baseline': cb,

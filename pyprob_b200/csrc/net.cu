@@ -51,8 +51,8 @@ struct ppb_net {
   std::vector<WImg> w1, w2;
   // content hashes of the problem lists last uploaded to each device region: identical lists are not re-sent,
   // which also makes a repeated step capturable in a CUDA graph (no host->device copy inside the capture)
-  uint64_t slot_hash[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const void* slot_dev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint64_t slot_hash[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const void* slot_dev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   void* h_blob[2] = {nullptr, nullptr};
   cudaEvent_t ev_blob[2] = {nullptr, nullptr};
   size_t blob_cap = 0;
@@ -74,6 +74,9 @@ struct ppb_net {
   size_t lstm_steps_cap = 0;        // bytes
   int* d_lstm_progress = nullptr;   // level 2: arrival counters (one per 128-row tile) + error flag
   int lstm_progress_cap = 0;        // ints
+  int fused_cell_bwd = 1;           // BPTT: input-gradient GEMM + cell backward in one cluster kernel (PPB_FUSED_CELL_BWD=0: off)
+  void* d_bsteps = nullptr;         // device list of tcc::BStep
+  size_t bsteps_cap = 0;            // bytes
   // side streams: independent branches of the step run beside the critical path (captured into the same CUDA graph)
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaEvent_t fork_ev[16] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
@@ -921,6 +924,8 @@ int ppb_net_create(ppb_net** out, const ppb_net_desc* d) {
   // LSTM steps t >= 1: 3 (default) = recurrent GEMM + cell in one kernel per step, cluster split-K when the step has few
   // tiles (tc_cluster.cuh); 1 = same without clusters; 2 = one persistent launch for all steps; 0 = GEMM and cell kernels
   n->fused_cell = (fc && fc[0] >= '0' && fc[0] <= '3') ? fc[0] - '0' : 3;
+  const char* fb = getenv("PPB_FUSED_CELL_BWD");
+  n->fused_cell_bwd = (fb && fb[0] == '0') ? 0 : 1;
   const char* ss = getenv("PPB_SINGLE_STREAM");
   n->single_stream = (ss && ss[0] == '1') ? 1 : 0;
   // created up front: a training step must be capturable in a CUDA graph right after its first eager run
@@ -974,6 +979,7 @@ int ppb_net_destroy(ppb_net* net) {
   if (net->whh_il) cudaFree(net->whh_il);
   if (net->d_lstm_steps) cudaFree(net->d_lstm_steps);
   if (net->d_lstm_progress) cudaFree(net->d_lstm_progress);
+  if (net->d_bsteps) cudaFree(net->d_bsteps);
   delete net;
   return PPB_OK;
 }

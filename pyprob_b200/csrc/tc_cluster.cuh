@@ -48,6 +48,28 @@ __device__ __forceinline__ float ld_cluster(uint32_t cluster_addr) {
   return v;
 }
 
+struct BwdIO {                // element-wise operands of the LSTM cell backward, shared by all segments of a launch
+  const float* gates;         // [rows, 4H] activated gates i, f, g, o (forward pass)
+  const float* c;             // [rows, H]
+  const float* dh;            // [rows, H]  d loss / d h_t from the proposal heads
+  float* dc;                  // [rows, H]  d loss / d c carried to the previous step
+  float* dgates;              // [rows, 4H] d loss / d gate pre-activations (fp32: column sums, sample-embedding gradients)
+  float* d_pobs;              // [traces, 4H] sum over the steps of a trace
+  const int* row_prev; const int* row_next; const int* row_trace;
+  float* gk_hi; float* gk_lo; float* gmn_hi; float* gmn_lo;   // tile images of dgates (next BPTT GEMM, weight gradients)
+  int gkb;                    // column blocks of the dgates images (4H / 32)
+  int H;
+};
+struct BStep {                // BPTT at time t for one (t + 1, sub-batch) segment: dh_rec = dgates_{t+1} W_hh, then the cell
+  tcg::Operand a;             // dgates image, rows of the segment at step t + 1 (K-major)
+  tcg::Operand b;             // W_hh image read MN-major (reduction over its 4H rows)
+  int M;                      // segment rows, padded to 128
+  int row0;                   // first global row of the segment at step t (multiple of 128)
+  int t;                      // time index of the rows being finished (c_{t-1} = 0 at t = 0)
+  int tile_start, tiles_m, tiles_n;
+  BwdIO io;
+};
+
 struct __align__(1024) Smem {
   float a_hi[tcg::kStages][kTileFloats];
   float a_lo[tcg::kStages][kTileFloats];
@@ -57,7 +79,7 @@ struct __align__(1024) Smem {
   uint64_t empty[tcg::kStages];
   uint64_t tmem_full;
   uint32_t tmem_base;
-  union { tcg::Problem prob; tcl::Step step; };
+  union { tcg::Problem prob; tcl::Step step; BStep bstep; };
 };
 inline size_t smem_bytes() { return sizeof(Smem) + 1024; }
 
@@ -129,9 +151,9 @@ __device__ __forceinline__ void mainloop_and_park(Smem& sm, const tcg::Operand& 
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = 0.0f;
     }
-    float* dst = part + (q * 32 + lane) * kPitch + cb * 32;
+    const uint32_t dst = smem_u32(part + (q * 32 + lane) * kPitch + cb * 32);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) dst[j] = v[j];
+    for (int j = 0; j < 32; ++j) asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + 4 * j), "f"(v[j]) : "memory");
   }
   fence_before_sync();
   cluster_sync_all();
@@ -325,6 +347,98 @@ __global__ void __launch_bounds__(tcg::kThreads, 1) k_lstm_cluster(const tcl::St
       const int64_t pos_mn = span + ((((lane >> 3) ^ (int)(row & 3))) << 3) + (lane & 7);
       tcg::st_global(io.hmn_hi + pos_mn, hh);
       tcg::st_global(io.hmn_lo + pos_mn, hl);
+    }
+  }
+  fence_before_sync();
+  cluster_sync_all();
+  if (warp == 1) {
+    fence_after_sync();
+    tmem_dealloc<tcg::kTmemCols>(tmem);
+  }
+}
+
+// ---- BPTT time step: recurrent input-gradient GEMM + cell backward in the reduce phase ----------------------------------------
+// Output tile = 128 rows of step t x 128 hidden units; a thread of the reduce phase holds dh_rec of one row and four units and
+// finishes them: d gates (fp32 + both image formats), d c_{t-1}, the per-trace sum d_pobs.  Mirrors k_cell_bwd (net.cu).
+template <bool X3, int CS>
+__global__ void __launch_bounds__(tcg::kThreads, 1) k_lstm_bwd_cluster(const BStep* __restrict__ steps, int n_steps) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x / CS;
+  const int split = (int)cluster_ctarank();
+  int lo_i = 0, hi_i = n_steps - 1;
+  while (lo_i < hi_i) {
+    int mid = (lo_i + hi_i + 1) >> 1;
+    if (steps[mid].tile_start <= tile) lo_i = mid; else hi_i = mid - 1;
+  }
+  for (int i = threadIdx.x; i < (int)(sizeof(BStep) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(&sm.bstep)[i] = reinterpret_cast<const uint32_t*>(steps + lo_i)[i];
+  __syncthreads();
+  const BStep& P = sm.bstep;
+  const BwdIO& io = P.io;
+  const int local = tile - P.tile_start;
+  const int mt = local / P.tiles_n, nt = local % P.tiles_n;   // nt = block of 128 hidden units
+  const int H = io.H, H4 = 4 * io.H;
+  const int KC = H4 / 32;
+  const int c0 = (int)((int64_t)KC * split / CS), c1 = (int)((int64_t)KC * (split + 1) / CS);
+  common_setup(sm, warp, lane);
+  const uint32_t tmem = sm.tmem_base;
+  mainloop_and_park<X3>(sm, P.a, P.b, mt, nt, c0, c1, tmem, warp, lane);
+
+  if (warp >= 2) {
+    constexpr int kRowsPerCta = 128 / CS, kRowsPerWarp = kRowsPerCta / tcg::kEpiWarps;
+    const int ew = warp - 2;
+    const int64_t gkb = io.gkb;
+#pragma unroll
+    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+      const int trow = split * kRowsPerCta + ew * kRowsPerWarp + rr;
+      const int64_t row = (int64_t)P.row0 + mt * 128 + trow;
+      const int tr = __ldg(io.row_trace + row);
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      int64_t nx = 0, rp = 0;
+      if (tr >= 0) {   // warp-uniform
+        reduce_row<CS>(sm, trow, lane, v);
+        nx = __ldg(io.row_next + row);
+        rp = (P.t > 0) ? __ldg(io.row_prev + row) : 0;
+      }
+      const int64_t img_row = ((row >> 7) * gkb) * kTileFloats + (row & 127) * 32;
+      const int pk = ((((lane >> 2) ^ (int)(row & 7))) << 2) + (lane & 3);
+      const int pmn = ((((lane >> 3) ^ (int)(row & 3))) << 3) + (lane & 7);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int u = nt * 128 + g * 32 + lane;
+        if (u - lane >= H) continue;   // warp-uniform: unit block beyond H (H < 128 * tiles_n)
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        if (tr >= 0) {
+          const float* gr = io.gates + row * H4;
+          const float ig = __ldg(gr + u), fg = __ldg(gr + H + u), gg = __ldg(gr + 2 * H + u), og = __ldg(gr + 3 * H + u);
+          const float cn = __ldg(io.c + row * H + u);
+          const float cp = (P.t > 0) ? __ldg(io.c + rp * H + u) : 0.0f;
+          const float tc = tanhf(cn);
+          const float dht = __ldg(io.dh + row * H + u) + v[g];
+          const float dct = tcg::ld_global(io.dc + nx * H + u) + dht * og * (1.0f - tc * tc);
+          d[0] = dct * gg * ig * (1.0f - ig);
+          d[1] = dct * cp * fg * (1.0f - fg);
+          d[2] = dct * ig * (1.0f - gg * gg);
+          d[3] = dht * tc * og * (1.0f - og);
+          tcg::st_global(io.dc + row * H + u, dct * fg);
+          float* dp = io.d_pobs + (int64_t)tr * H4;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) tcg::st_global(dp + q * H + u, tcg::ld_global(dp + q * H + u) + d[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          tcg::st_global(io.dgates + row * H4 + q * H + u, d[q]);
+          const int64_t span = img_row + (int64_t)((q * H + u - lane) >> 5) * kTileFloats;
+          float hh, hl;
+          split_tf32(d[q], hh, hl);
+          tcg::st_global(io.gk_hi + span + pk, hh);
+          tcg::st_global(io.gk_lo + span + pk, hl);
+          tcg::st_global(io.gmn_hi + span + pmn, hh);
+          tcg::st_global(io.gmn_lo + span + pmn, hl);
+        }
+      }
     }
   }
   fence_before_sync();

@@ -722,11 +722,19 @@ class InferenceNetworkLSTM(nn.Module):
                 self._history_valid_loss.append(valid_loss)
                 self._history_valid_loss_trace.append(self._total_train_traces)
                 last_validation_trace = trace - 1
-            if rank == 0 and save_file_name_prefix is not None and save_every_sec is not None:
-                if time_batch - last_save > save_every_sec:
+            if save_file_name_prefix is not None and save_every_sec is not None:
+                want_save = rank == 0 and time_batch - last_save > save_every_sec
+                if world > 1 and self._peer is not None:
+                    # the optimiser moments are sharded over the ranks: saving is a collective, rank 0's clock decides
+                    flag = torch.tensor([1 if want_save else 0], dtype=torch.int32, device=self._arena.device)
+                    dist.broadcast(flag, 0)
+                    want_save = bool(int(flag))
+                if want_save:
                     last_save = time_batch
-                    self._save('{}_{}_traces_{}.network'.format(save_file_name_prefix, util.get_time_stamp(),
-                                                               self._total_train_traces))
+                    moments = self._full_optimizer_moments()
+                    if rank == 0:
+                        self._save('{}_{}_traces_{}.network'.format(save_file_name_prefix, util.get_time_stamp(),
+                                                                   self._total_train_traces), moments)
             if trace >= num_traces:
                 stop = True
             if util._verbosity > 1 and (stop or self._total_train_iterations % 50 == 0):
@@ -740,9 +748,11 @@ class InferenceNetworkLSTM(nn.Module):
                     getattr(dataset, 'current_bucket_id', None), traces_per_second))
         if log_file is not None:
             log_file.close()
-        if rank == 0 and save_file_name_prefix is not None:
-            self._save('{}_{}_traces_{}.network'.format(save_file_name_prefix, util.get_time_stamp(),
-                                                       self._total_train_traces))
+        if save_file_name_prefix is not None:
+            moments = self._full_optimizer_moments()   # collective under the fused data-parallel step
+            if rank == 0:
+                self._save('{}_{}_traces_{}.network'.format(save_file_name_prefix, util.get_time_stamp(),
+                                                           self._total_train_traces), moments)
 
     def _validation_loss(self, dataset_valid, batch_size, world):
         """Mean minibatch loss over one pass of the validation set (reference inference_network.py:534-546): the
@@ -781,12 +791,45 @@ class InferenceNetworkLSTM(nn.Module):
     # ------------------------------------------------------------------------------------------------
     # checkpoint (reference: inference_network.py:162-263)
     # ------------------------------------------------------------------------------------------------
-    def _save(self, file_name):
+    def _owned_slice(self, n, world, rank):
+        """[lo, hi) of the flat arena whose optimiser state lives on `rank` under the fused data-parallel step
+        (same split as k_dp_adam, csrc/dp.cu: ceil(n / 4 world) float4 blocks per rank)."""
+        per = ((n + world * 4 - 1) // (world * 4)) * 4
+        lo = min(n, rank * per)
+        return lo, min(n, lo + per)
+
+    def _full_optimizer_moments(self):
+        """(exp_avg, exp_avg_sq) of the WHOLE arena.  With the fused data-parallel step every rank only ever updates the
+        moments of the slice it owns; a checkpoint needs all of them, so the owned slices are summed over the ranks (each
+        element is non-zero on exactly one rank).  COLLECTIVE when training data-parallel: every rank must call it."""
+        if self._exp_avg is None:
+            return None, None
+        if self._peer is None:
+            return self._exp_avg, self._exp_avg_sq
+        import torch.distributed as dist
+        world, rank = parallel.world_info()
+        n = self._exp_avg.numel()
+        lo, hi = self._owned_slice(n, world, rank)
+        out = []
+        for t in (self._exp_avg, self._exp_avg_sq):
+            full = torch.zeros_like(t)
+            full[lo:hi] = t[lo:hi]
+            if world > 1:
+                dist.all_reduce(full)
+            out.append(full)
+        return out[0], out[1]
+
+    def _save(self, file_name, moments=None):
+        """Write a checkpoint.  Data-parallel training over NVLink peer memory: call `_full_optimizer_moments()` on EVERY
+        rank first and pass the result on the rank that writes (optimize() does this); a direct call on one rank falls
+        back to that rank's local arrays."""
         self._modified = util.get_time_str()
         self._updates += 1
+        m, v = moments if moments is not None else (
+            self._full_optimizer_moments() if parallel.world_info()[0] == 1 else (self._exp_avg, self._exp_avg_sq))
         data = {'pyprob_b200_version': 1, 'torch_version': torch.__version__, 'inference_network': self,
                 'optimizer_state': None if self._exp_avg is None else
-                {'exp_avg': self._exp_avg.cpu(), 'exp_avg_sq': self._exp_avg_sq.cpu(), 'step': self._optimizer_step,
+                {'exp_avg': m.cpu(), 'exp_avg_sq': v.cpu(), 'step': self._optimizer_step,
                  'segment_steps': None if self._seg is None else self._seg['steps'].cpu()}}
         torch.save(data, file_name)
 
@@ -836,6 +879,38 @@ class InferenceNetworkLSTM(nn.Module):
              need, stream())
         self._infer_observe_embedding = emb
         self._infer_state = None
+
+    def _address_by_id(self):
+        """address id -> address string (ids are insertion order of `_addresses`)."""
+        cache = getattr(self, '_by_id_cache', None)
+        if cache is None or len(cache) != len(self._addresses):
+            cache = {info['id']: a for a, info in self._addresses.items()}
+            self._by_id_cache = cache
+        return cache
+
+    def _infer_step_lanes(self, address, prev_address, prev_value, prior0, prior1, h, c):
+        """One proposal step for the particles whose LSTM state rows are `h`, `c` ([m, H] contiguous, updated in place):
+        all m particles sit at `address` and came from `prev_address` (None: first controlled site) with values
+        `prev_value` [m].  Returns the proposal parameters [m, 3K] (means|stddevs|probs) or [m, C]."""
+        info = self._addresses[address]
+        m = h.size(0)
+        width = info['head_out'] if info['family'] != FAMILY_CATEGORICAL else info['num_categories']
+        params = torch.empty(m, width, dtype=torch.float32, device='cuda')
+        need = self._infer_workspace(m)
+
+        def par(x):
+            if x is None:
+                return None, 0, None
+            t = torch.as_tensor(x, dtype=torch.float32, device='cuda').reshape(-1).contiguous()
+            return t, (0 if t.numel() == 1 else 1), t
+        p0, s0, k0 = par(prior0)
+        p1, s1, k1 = par(prior1)
+        pv = None if prev_value is None else prev_value.to(dtype=torch.float32).contiguous()
+        call('ppb_ic_infer_step', self._handle, ptr(self._arena.data), ptr(self._infer_observe_embedding), 0,
+             -1 if prev_address is None else self._addresses[prev_address]['id'], ptr(pv), info['id'],
+             ptr(p0), s0, ptr(p1), s1, ptr(h), ptr(c), ptr(params), m, ptr(self._infer_ws), need, self._precision,
+             stream())
+        return params
 
     def _infer_step_batched(self, address, prev_address, prev_value, prior0, prior1, n):
         """Proposal parameters for n particles in lock-step at `address`.

@@ -9,6 +9,7 @@ sampled tensor still works — the engine falls back to one particle per executi
 import dis
 import sys
 import time
+import warnings
 
 import torch
 
@@ -96,9 +97,9 @@ def _accumulate(trace, fn):
     if _mask is None:
         fn(trace.log_w)
     else:
-        tmp = trace.log_w.clone()
-        fn(tmp)
-        trace.log_w = torch.where(_mask, tmp, trace.log_w)
+        term = torch.zeros_like(trace.log_w)
+        fn(term)
+        trace.log_w.add_(term.masked_fill_(~_mask, 0.0))   # masked-out lanes may hold junk (even NaN): dropped
 
 
 def _prior_params(distribution):
@@ -185,42 +186,124 @@ def sample(distribution, name=None, address=None, control=True):
     return value
 
 
-def _sample_from_proposal(trace, distribution, addr, n):
-    """IC branch (state.py:203-219): value ~ q(.|LSTM state); weight += log p(value) - log q(value)."""
-    net = _network
-    prev = _previous_site
-    p0, p1 = _prior_params(distribution)
-    keep = None
-    if _mask is not None and net._infer_state is not None:
-        keep = (net._infer_state[0].clone(), net._infer_state[1].clone())
-    params = net._infer_step_batched(addr, None if prev is None else prev.address,
-                                     None if prev is None else prev.value, p0, p1, n)
-    if params is None:
-        return distribution.sample(n)  # unknown address: propose from the prior, weight term zero
-    if keep is not None:  # lanes outside the mask keep their LSTM state
-        h, c = net._infer_state
-        m = _mask.view(-1, 1)
-        h.copy_(torch.where(m, h, keep[0]))
-        c.copy_(torch.where(m, c, keep[1]))
-    K = net._proposal_mixture_components
-    if isinstance(distribution, Categorical):
-        proposal = Categorical(probs=params)
-    elif isinstance(distribution, Normal):
-        proposal = Mixture.from_rows(params[:, :K], params[:, K:2 * K], params[:, 2 * K:])
-    elif isinstance(distribution, Uniform):
-        proposal = Mixture.from_rows(params[:, :K], params[:, K:2 * K], params[:, 2 * K:], distribution.low,
-                                     distribution.high)
-    elif isinstance(distribution, Poisson):
-        proposal = Mixture.from_rows(params[:, :K], params[:, K:2 * K], params[:, 2 * K:], 0.0, 40.0)
-    else:
-        raise RuntimeError('Distribution currently unsupported: {}'.format(distribution.name))
-    value, q_lp = proposal.sample(n, with_log_prob=True)
+def _lanes(x, idx):
+    """Rows `idx` of a per-particle parameter (tensors only; scalars are shared by all particles)."""
+    return x[idx] if (torch.is_tensor(x) and x.numel() > 1 and idx is not None) else x
 
-    def fn(acc):
-        distribution.score_into(value, acc, 1.0)
-        acc.sub_(q_lp.double())
-    _accumulate(trace, fn)
+
+def _sample_from_proposal(trace, distribution, addr, n):
+    """IC branch (state.py:203-219): value ~ q(.|LSTM state); weight += log p(value) - log q(value).
+
+    The proposal network only runs for the particles that execute this statement (the lanes of the current mask), packed
+    densely, so a loop whose lanes drop out costs what its live lanes cost.  Every lane keeps its own LSTM state and its
+    own previous site (address id + value): lanes that reached this statement from different sites are stepped in
+    separate groups, like the per-trace `_current_trace_previous_variable` of the reference (state.py:212)."""
+    net = _network
+    H, K = net._lstm_dim, net._proposal_mixture_components
+    st = trace.ic_state
+    if st is None:
+        st = trace.ic_state = {'h': torch.zeros(n, H, device='cuda'), 'c': torch.zeros(n, H, device='cuda'),
+                               'prev_id': torch.full((n,), -1, dtype=torch.int64, device='cuda'),
+                               'prev_value': torch.zeros(n, device='cuda'),
+                               'uniform_prev': -1}    # host copy of prev_id when all lanes are known to share it
+    known = addr in net._addresses
+    if not known:
+        warnings.warn('Address unknown by inference network: {}'.format(addr))
+    idx = None if _mask is None else torch.nonzero(_mask).view(-1)
+    p0, p1 = _prior_params(distribution)
+    # group the executing lanes by the site they came from
+    if idx is None and st['uniform_prev'] is not None:
+        groups = [(st['uniform_prev'], None)]
+    else:
+        ids = st['prev_id'] if idx is None else st['prev_id'][idx]
+        uniq = torch.unique(ids).tolist()
+        groups = [(u, None if len(uniq) == 1 else (ids == u)) for u in uniq]
+    is_cat = isinstance(distribution, Categorical)
+    width = distribution.num_categories if is_cat else 3 * K
+    params = None
+    covered = True        # every executing lane got a proposal from the network
+    by_id = net._address_by_id()
+    for pid, sel in groups:
+        if not known or pid == -2 or (pid >= 0 and pid not in by_id):
+            covered = False
+            continue
+        lanes = idx if sel is None else (torch.nonzero(sel).view(-1) if idx is None else idx[sel])
+        if lanes is None:
+            h, c = st['h'], st['c']
+            pv = st['prev_value']
+        else:
+            h, c = st['h'][lanes], st['c'][lanes]
+            pv = st['prev_value'][lanes]
+        out = net._infer_step_lanes(addr, None if pid < 0 else by_id[pid], None if pid < 0 else pv, _lanes(p0, lanes),
+                                    _lanes(p1, lanes), h, c)
+        if lanes is None:
+            params = out
+        else:
+            st['h'].index_copy_(0, lanes, h)
+            st['c'].index_copy_(0, lanes, c)
+            if params is None:
+                params = _default_params(distribution, n, K, width)
+            params.index_copy_(0, lanes, out)
+    if params is None:   # nobody could be proposed for: prior proposal, weight term exactly zero (reference warning path)
+        value = distribution.sample(n)
+    else:
+        if is_cat:
+            proposal = Categorical(probs=params)
+        elif isinstance(distribution, Normal):
+            proposal = Mixture.from_rows(params[:, :K], params[:, K:2 * K], params[:, 2 * K:])
+        elif isinstance(distribution, Uniform):
+            proposal = Mixture.from_rows(params[:, :K], params[:, K:2 * K], params[:, 2 * K:], distribution.low,
+                                         distribution.high)
+        elif isinstance(distribution, Poisson):
+            proposal = Mixture.from_rows(params[:, :K], params[:, K:2 * K], params[:, 2 * K:], 0.0, 40.0)
+        else:
+            raise RuntimeError('Distribution currently unsupported: {}'.format(distribution.name))
+        value, q_lp = proposal.sample(n, with_log_prob=True)
+        if not covered:   # lanes whose previous / current address the network does not know fall back to the prior
+            has = torch.zeros(n, dtype=torch.bool, device='cuda')
+            for pid, sel in groups:
+                if known and pid != -2 and (pid < 0 or pid in by_id):
+                    lanes = idx if sel is None else (torch.nonzero(sel).view(-1) if idx is None else idx[sel])
+                    if lanes is None:
+                        has.fill_(True)
+                    else:
+                        has[lanes] = True
+            prior_value, prior_lp = distribution.sample(n, with_log_prob=True)
+            value = torch.where(has, value, prior_value)
+            q_lp = torch.where(has, q_lp, prior_lp)
+
+        def fn(acc):
+            distribution.score_into(value, acc, 1.0)
+            acc.sub_(q_lp.double())
+        _accumulate(trace, fn)
+    # this site becomes the previous site of the lanes that executed it
+    new_id = net._addresses[addr]['id'] if known else -2
+    if idx is None:
+        st['prev_id'].fill_(new_id)
+        st['prev_value'] = value.to(torch.float32).clone()
+        st['uniform_prev'] = new_id
+    else:
+        st['prev_id'].index_fill_(0, idx, new_id)
+        st['prev_value'].index_copy_(0, idx, value.to(torch.float32)[idx])
+        st['uniform_prev'] = None
     return value
+
+
+def _default_params(distribution, n, K, width):
+    """Benign proposal parameters for lanes that do not execute the statement (their draws are discarded by the mask)."""
+    p = torch.zeros(n, width, device='cuda')
+    if isinstance(distribution, Categorical):
+        p.fill_(1.0 / width)
+    else:
+        if isinstance(distribution, Uniform):
+            lo, hi = distribution.low, distribution.high
+            mid = (lo + hi) / 2
+            p[:, :K] = mid.view(-1, 1) if torch.is_tensor(mid) else mid
+        elif isinstance(distribution, Poisson):
+            p[:, :K] = 1.0
+        p[:, K:2 * K] = 1.0
+        p[:, 2 * K:] = 1.0 / K
+    return p
 
 
 def while_loop(cond_fn, body_fn, state, max_iterations=10000):

@@ -41,6 +41,7 @@ class BatchedTrace:
         self.log_w = torch.zeros(n, dtype=torch.float64, device='cuda')  # per-particle log importance weight
         self.result = None
         self.execution_time_sec = None
+        self.ic_state = None   # per-lane LSTM state and previous site of the proposal network (state._sample_from_proposal)
 
     def add(self, site):
         self.sites.append(site)

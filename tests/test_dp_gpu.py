@@ -160,3 +160,68 @@ def test_peer_adam_matches_allreduce_adam(use_graph):
             p.kill()
             pytest.fail('worker did not finish')
         assert p.exitcode == 0
+
+
+def _checkpoint_worker(rank, world, port, path):
+    """Data-parallel training keeps the Adam moments of an element on its owning rank only; a checkpoint must hold all of
+    them: _full_optimizer_moments gathers the owned slices, save -> load restores the full arrays."""
+    import torch.distributed as dist
+    from pyprob_b200 import synthetic
+    from pyprob_b200.network import InferenceNetworkLSTM
+    from pyprob_b200.util import Optimizer
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    net = synthetic.gum_network(lstm_dim=32, seed=0)
+    net._optimizer_type, net._learning_rate_init, net._weight_decay = Optimizer.ADAM, 1e-3, 1e-5
+    net._create_optimizer()
+    net._learning_rate = 1e-3
+    dist.broadcast(net._arena.data, 0)
+    p0 = net._arena.data.clone()
+    net._enable_peer_optimizer()
+    n = net._arena.numel()
+    gen = torch.Generator(device='cpu').manual_seed(3)
+    all_grads = [[torch.randn(n, generator=gen) for _ in range(world)] for _ in range(STEPS)]
+    summed = []
+    for step in all_grads:
+        g = step[rank].to(dev)
+        dist.all_reduce(g)
+        summed.append(g)
+    want_p, want_m, want_v = _reference_steps(p0, summed, world, dev)
+    for step in all_grads:
+        net._arena.grad = step[rank].to(dev)
+        net._peer_optimizer_step(torch.tensor(1.0, device=dev), world)
+    m, v = net._full_optimizer_moments()
+    tol = dict(rtol=0, atol=0) if world == 2 else dict(rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(m, want_m, **tol)
+    torch.testing.assert_close(v, want_v, **tol)
+    if rank == 0:
+        net._save(path, (m, v))
+        loaded = InferenceNetworkLSTM._load(path)
+        assert torch.equal(loaded._exp_avg, m) and torch.equal(loaded._exp_avg_sq, v)
+        assert loaded._optimizer_step == STEPS
+        torch.testing.assert_close(loaded._arena.data, want_p, rtol=1e-5, atol=1e-6)
+    dist.barrier()
+    torch.cuda.synchronize()
+    os._exit(0)
+
+
+def test_checkpoint_holds_the_moments_of_every_rank(tmp_path):
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip('needs at least two GPUs on one NVLink node')
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    port = _free_port()
+    procs = [ctx.Process(target=_checkpoint_worker, args=(r, world, port, str(tmp_path / 'dp.network'))) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+    for p in procs:
+        if p.is_alive():
+            p.kill()
+            pytest.fail('worker did not finish')
+        assert p.exitcode == 0

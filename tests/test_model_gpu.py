@@ -150,3 +150,42 @@ def test_online_minibatches_are_disjoint_between_ranks(cuda, monkeypatch):
     monkeypatch.setattr(parallel, 'world_info', lambda: (1, 0))
     full = OnlineDataset(model).next_batch(128).trace.variables_controlled[0].value.cpu()
     assert torch.equal(torch.cat(halves), full)
+
+
+class DivergingPaths(Model):
+    """Lanes reach the last site from DIFFERENT previous sites: half of them run an extra masked statement."""
+
+    def forward(self):
+        a = pyprob.sample(Uniform(0, 1))
+        st = pyprob.while_loop(lambda s: s['todo'] > 0,
+                               lambda s: {'b': pyprob.sample(Normal(2.0, 1.0)), 'todo': s['todo'] * 0},
+                               {'b': 0.0, 'todo': (a > 0.5).float()})
+        c = pyprob.sample(Normal(st['b'] + a, 1.0))
+        pyprob.observe(Normal(c, 0.5), name='obs')
+        return c
+
+
+def test_ic_weights_follow_each_lanes_own_previous_site(cuda):
+    """Per-lane previous site / LSTM state in lock-step IC: particles that skipped the masked statement
+    must be conditioned on the site THEY executed last, exactly like one reference trace each (state.py:203-219)."""
+    from pyprob_b200.util import TraceMode
+    from tests.ic_replay import site_weight_terms
+    pyprob.seed(31)
+    pyprob.set_verbosity(0)
+    model = DivergingPaths()
+    model.learn_inference_network(num_traces=30 * 256, batch_size=256, inference_network=InferenceNetwork.LSTM, lstm_dim=64,
+                                  observe_embeddings={'obs': {'dim': 16}})
+    net = model._inference_network
+    n = 2000
+    with torch.no_grad():
+        trace = model._run_batched(n, trace_mode=TraceMode.POSTERIOR,
+                                   inference_engine=InferenceEngine.IMPORTANCE_SAMPLING_WITH_INFERENCE_NETWORK,
+                                   inference_network=net, observe={'obs': 3.0})
+    want, covered = site_weight_terms(trace, net, torch.tensor([3.0]))
+    assert covered.all()
+    c = trace.result.cpu()
+    want = want + scoring.normal_log_prob(torch.tensor(3.0), c, torch.tensor(0.5)).double().numpy()
+    got = trace.log_w.cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-4)
+    took_b = trace.variables_controlled[1].mask.cpu().numpy()
+    assert 0.3 < took_b.mean() < 0.7      # both kinds of lanes are present
