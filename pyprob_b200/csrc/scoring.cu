@@ -149,6 +149,51 @@ __global__ void __launch_bounds__(kThreads) k_categorical(const float* __restric
 // ---- mixtures ------------------------------------------------------------------------------------
 // Mixture.log_prob (pyprob/distributions/mixture.py:15-16, :38-45):
 //   w = probs / sum(probs); lw = log(clamp(w)); lp = logsumexp_k(lw_k + lp_k(v))
+// Arithmetic: with w_k = clamp(p_k / sum p) and z_k = (v - mu_k) / sigma_k,
+//   logsumexp_k(log w_k + log N(v; mu_k, sigma_k)) = max_k(-z_k^2 / 2) + log sum_k (w_k / sigma_k) exp(-z_k^2 / 2 - max) - log sqrt(2 pi)
+// (truncated components: sigma_k -> sigma_k Z_k, and -inf outside [low, high]): one exp and one reciprocal per component and
+// ONE log per particle instead of two logs, an exp and two divisions per component — these kernels are bound by the
+// transcendental/ALU rate, not by HBM (ncu: profiles/).  Same value as the reference's formula up to fp32 rounding.
+template <int KMAX, bool TRUNC>
+__device__ __forceinline__ float mixture_row(float v, const float* __restrict__ m, const float* __restrict__ s,
+                                             const float* __restrict__ p, int K, float lo, float hi) {
+  float pk[KMAX], a[KMAX], scale[KMAX];
+  float psum = 0.0f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    pk[k] = (k < K) ? p[k] : 0.0f;
+    psum += pk[k];
+  }
+  const float inv_psum = 1.0f / psum;
+  float mx = -INFINITY;
+  bool any_nan = false;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    if (k < K) {
+      const float mu = m[k], sg = s[k];
+      const float inv_sg = 1.0f / sg;
+      const float z = (v - mu) * inv_sg;
+      float norm = sg;                       // sigma (times the truncated mass)
+      if (TRUNC) {
+        const float alpha = (lo - mu) * inv_sg, beta = (hi - mu) * inv_sg;
+        norm = sg * (ppb_std_normal_cdf(beta) - ppb_std_normal_cdf(alpha));
+      }
+      a[k] = -0.5f * z * z;
+      scale[k] = ppb_clamp_prob(pk[k] * inv_psum) / norm;
+      any_nan = any_nan || (a[k] != a[k]) || (scale[k] != scale[k]) || !(norm >= 0.0f);
+      mx = fmaxf(mx, a[k]);
+    }
+  }
+  if (any_nan) return NAN;                   // log of a negative / NaN parameter poisons the row like the reference
+  if (TRUNC && !(v >= lo && v <= hi)) return -INFINITY;   // log(lb * ub) = -inf in every component
+  if (mx == -INFINITY) return -INFINITY;     // torch.logsumexp of all -inf
+  float acc = 0.0f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k)
+    if (k < K) acc += scale[k] * expf(a[k] - mx);
+  return mx + logf(acc) - PPB_LOG_SQRT_2PI;
+}
+
 template <int KMAX, bool TRUNC>
 __global__ void __launch_bounds__(kThreads) k_mixture(const float* __restrict__ value,
                                                        const float* __restrict__ means,
@@ -158,39 +203,10 @@ __global__ void __launch_bounds__(kThreads) k_mixture(const float* __restrict__ 
   int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t nth = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = tid; i < n; i += nth) {
-    const float* m = means + i * row_stride;
-    const float* s = stddevs + i * row_stride;
-    const float* p = probs + i * row_stride;
-    float v = __ldg(value + i);
     float lo = 0.f, hi = 0.f;
     if (TRUNC) { lo = low.at(i); hi = high.at(i); }
-    float t[KMAX];
-    float psum = 0.0f;
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k)
-      if (k < K) psum += __ldg(p + k);
-    float mx = -INFINITY;
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      if (k < K) {
-        float lw = logf(ppb_clamp_prob(__ldg(p + k) / psum));
-        float mu = __ldg(m + k), sg = __ldg(s + k);
-        float lpk = TRUNC ? ppb_truncnormal_lp(v, mu, sg, lo, hi) : ppb_normal_lp(v, mu, sg);
-        t[k] = lw + lpk;
-        mx = fmaxf(mx, t[k]);
-      }
-    }
-    float r;
-    if (mx == -INFINITY) {
-      r = -INFINITY;  // torch.logsumexp of all -inf
-    } else {
-      float acc = 0.0f;
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k)
-        if (k < K) acc += expf(t[k] - mx);
-      r = mx + logf(acc);
-    }
-    out.put(i, r);
+    out.put(i, mixture_row<KMAX, TRUNC>(__ldg(value + i), means + i * row_stride, stddevs + i * row_stride,
+                                        probs + i * row_stride, K, lo, hi));
   }
 }
 
@@ -234,34 +250,9 @@ __global__ void __launch_bounds__(kThreads) k_mixture_staged(const float* __rest
       const float* m = sm_m + threadIdx.x * K;
       const float* sd = sm_s + threadIdx.x * K;
       const float* p = sm_p + threadIdx.x * K;
-      float v = __ldg(value + i);
       float lo = 0.f, hi = 0.f;
       if (TRUNC) { lo = low.at(i); hi = high.at(i); }
-      float t[KMAX];
-      float psum = 0.0f;
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k)
-        if (k < K) psum += p[k];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k) {
-        if (k < K) {
-          float lw = logf(ppb_clamp_prob(p[k] / psum));
-          float lpk = TRUNC ? ppb_truncnormal_lp(v, m[k], sd[k], lo, hi) : ppb_normal_lp(v, m[k], sd[k]);
-          t[k] = lw + lpk;
-          mx = fmaxf(mx, t[k]);
-        }
-      }
-      float r;
-      if (mx == -INFINITY) {
-        r = -INFINITY;
-      } else {
-        float acc = 0.0f;
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k)
-          if (k < K) acc += expf(t[k] - mx);
-        r = mx + logf(acc);
-      }
+      const float r = mixture_row<KMAX, TRUNC>(__ldg(value + i), m, sd, p, K, lo, hi);
       out.put(i, r);
     }
     __syncthreads();

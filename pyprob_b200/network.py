@@ -494,6 +494,7 @@ class InferenceNetworkLSTM(nn.Module):
         self._optimizer_step = 0
         self._learning_rate = self._learning_rate_init
         self._seg = None
+        self._present_sig = None
         if self._optimizer_type != Optimizer.ADAM or self._skip_absent_gradients:
             self._create_segment_state()
         if state is not None:
@@ -507,7 +508,7 @@ class InferenceNetworkLSTM(nn.Module):
         """Device tables of the segment-aware optimiser step (ppb_optimizer_step_segmented): one segment per parameter
         tensor of the reference.  Needed for LARC / SGD (per-tensor norms, per-tensor first-step flag) and for the
         reference's skipping of tensors whose gradient is absent from a minibatch (`_skip_absent_gradients`)."""
-        names = sorted(self.parameter_index, key=lambda k: self.parameter_index[k][0])
+        names = self._segment_names()
         n = self._arena.numel()
         seg_of_block = np.full((n + 3) // 4, -1, dtype=np.int32)
         for k, name in enumerate(names):
@@ -522,21 +523,24 @@ class InferenceNetworkLSTM(nn.Module):
                      'scratch': torch.empty(int(scratch), dtype=torch.uint8, device='cuda'),
                      'hyper': torch.zeros(10, dtype=torch.float32, device='cuda')}
 
-    def _segment_presence(self, enc):
+    def _segment_names(self):
+        return sorted(self.parameter_index, key=lambda k: self.parameter_index[k][0])
+
+    def _segment_presence(self, enc, force=False):
         """int32[S]: 1 for every parameter tensor that took part in the forward pass of the encoded minibatch, i.e.
         whose .grad the reference's autograd would populate (all others stay None and are skipped by torch.optim):
         shared layers always; address / type embeddings and the proposal head of every address in the batch; the
         sample-embedding layer of every address that is some step's PREVIOUS address (inference_network_lstm.py:
         150-182)."""
-        seg = self._seg
-        present = np.ones(len(seg['names']), dtype=np.int32)
-        if not self._skip_absent_gradients or enc is None:
+        names = self._seg['names'] if self._seg is not None else self._segment_names()
+        present = np.ones(len(names), dtype=np.int32)
+        if (not self._skip_absent_gradients and not force) or enc is None:
             return present
         by_id = {info['id']: (a, info) for a, info in self._addresses.items()}
         cur = set(int(i) for i in np.unique(enc.arrays['step_addr']))
         prev = set(int(i) for i in np.unique(enc.arrays['step_prev_addr']) if i >= 0)
         types = set(by_id[i][1]['type'] for i in cur | prev)
-        for k, name in enumerate(seg['names']):
+        for k, name in enumerate(names):
             if name.startswith('_layers_address_embedding.'):
                 a = name[len('_layers_address_embedding.'):]
                 present[k] = int(self._addresses[a]['id'] in cur)
@@ -582,7 +586,33 @@ class InferenceNetworkLSTM(nn.Module):
                 self._learning_rate_end
         return self._learning_rate_init
 
+    def _maybe_switch_to_segmented(self):
+        """torch.optim skips parameter tensors whose gradient is absent from a minibatch (no moment decay, no step count,
+        no weight decay) — the reference's behaviour on torch >= 2.0 (inference_network.py:343-355, zero_grad sets None).
+        The flat Adam kernel treats an absent gradient as zeros, which is the same thing exactly as long as (a) the set of
+        absent tensors never changes and (b) weight decay is zero.  The first time either fails, training continues on the
+        segment-aware step (csrc/optim.cu) with the per-tensor step counts the history implies — no difference to the
+        reference is ever applied."""
+        if (self._seg is not None or self._optimizer_type != Optimizer.ADAM or self._peer is not None
+                or self._last_enc is None or parallel.world_info()[0] > 1):
+            return
+        present = self._segment_presence(self._last_enc, force=True)
+        sig = present.tobytes()
+        first = getattr(self, '_present_sig', None)
+        if first is None:
+            self._present_sig = sig
+            if present.all() or not float(self._weight_decay or 0.0):
+                return
+        elif sig == first:
+            return
+        before = np.frombuffer(self._present_sig, dtype=np.int32)
+        self._skip_absent_gradients = True
+        self._create_segment_state()
+        steps = torch.from_numpy(before.astype(np.int64) * int(self._optimizer_step))
+        self._seg['steps'].copy_(steps)
+
     def optimizer_step(self, grad_scale=1.0):
+        self._maybe_switch_to_segmented()
         self._optimizer_step += 1
         if self._seg is not None:
             self._segmented_optimizer_step(grad_scale)

@@ -34,17 +34,23 @@ _target_cache = {}
 
 # ---- addressing (same information content as the reference's bytecode addresses, state.py:31-84) --------
 def _assignment_target(code, lasti):
+    """What the statement does with the value of the sample/observe call at bytecode offset `lasti` (reference
+    `_extract_target_of_assignment`, pyprob/state.py:53-84): a variable name, 'return', ('subscr', base, index source) for
+    ``base[i] = pyprob.sample(...)`` with a constant or local-variable index, or None."""
     key = (code, lasti)
     if key not in _target_cache:
         target = None
-        for ins in dis.get_instructions(code):
-            if ins.offset <= lasti or ins.opname in ('CACHE', 'PRECALL', 'NOP'):
-                continue
-            if ins.opname in ('STORE_FAST', 'STORE_NAME', 'STORE_GLOBAL', 'STORE_DEREF'):
-                target = ins.argval
-            elif ins.opname in ('RETURN_VALUE',):
+        ins = [i for i in dis.get_instructions(code) if i.offset > lasti and i.opname not in ('CACHE', 'PRECALL', 'NOP')]
+        if ins:
+            first = ins[0]
+            if first.opname in ('STORE_FAST', 'STORE_NAME', 'STORE_GLOBAL', 'STORE_DEREF'):
+                target = first.argval
+            elif first.opname == 'RETURN_VALUE':
                 target = 'return'
-            break
+            elif (first.opname in ('LOAD_FAST', 'LOAD_NAME', 'LOAD_GLOBAL') and len(ins) >= 3
+                  and ins[1].opname in ('LOAD_CONST', 'LOAD_FAST') and ins[2].opname == 'STORE_SUBSCR'):
+                src = ('const', ins[1].argval) if ins[1].opname == 'LOAD_CONST' else ('fast', ins[1].argval)
+                target = ('subscr', first.argval, src)
         _target_cache[key] = target
     return _target_cache[key]
 
@@ -53,6 +59,10 @@ def _extract_address(depth=2):
     frame = sys._getframe(depth)
     ip = frame.f_lasti
     target = _assignment_target(frame.f_code, ip)
+    if isinstance(target, tuple):      # base[index] = ...: only integer indices name a target (reference :77-81)
+        _, base, (kind, arg) = target
+        index = arg if kind == 'const' else frame.f_locals.get(arg)
+        target = '{}[{}]'.format(base, index) if type(index) is int else None
     names = []
     f = frame
     while f is not None:

@@ -114,3 +114,38 @@ def test_adam_larc_trains_through_the_public_api(cuda, monkeypatch):
                                   lstm_dim=64, optimizer_type=Optimizer.ADAM_LARC, learning_rate_init=1e-3)
     hist = model._inference_network._history_train_loss
     assert len(hist) == 30 and np.all(np.isfinite(hist)) and np.mean(hist[-5:]) < np.mean(hist[:5])
+
+
+def test_flat_adam_switches_to_skipping_when_the_present_set_changes(cuda):
+    """Default Optimizer.ADAM through the flat-arena kernel must follow torch.optim.Adam with grad = None for the tensors a
+    minibatch does not touch (the reference on torch >= 2.0): identical while the set of touched tensors is constant, and
+    from the first change on through the segment-aware step with the step counts the history implies."""
+    from pyprob_b200 import synthetic
+    from pyprob_b200.util import Optimizer
+    table = [('a_n', 'Normal', 0), ('a_u', 'Uniform', 0), ('a_c', 'Categorical', 4)]
+    net = synthetic.build_network({'o0': {'dim': 8, 'depth': 2}}, [2], table, lstm_dim=32, mixture_components=3, seed=3)
+    net._optimizer_type, net._learning_rate_init, net._weight_decay = Optimizer.ADAM, 1e-3, 0.0
+    net._create_optimizer()
+    rng = np.random.default_rng(8)
+    full = synthetic.ArrayBatch([synthetic.random_sub_batch(rng, table, 20, 2)])
+    part = synthetic.ArrayBatch([synthetic.random_sub_batch(rng, table[:2], 12, 2)])
+    names = net._segment_names()
+    ref = {k: net.view(k).clone().requires_grad_(True) for k in names}
+    opt = torch.optim.Adam([ref[k] for k in names], lr=1e-3)
+    switched_at = None
+    for it, batch in enumerate((full, full, part, full, part, full)):
+        net._arena.grad = None
+        ok, loss = net._loss(batch)
+        assert ok
+        loss.backward()
+        present = net._segment_presence(net._last_enc, force=True)
+        for k, name in enumerate(names):
+            ref[name].grad = net.grad_view(name).clone() if present[k] else None
+        opt.step()
+        net.optimizer_step()
+        if net._seg is not None and switched_at is None:
+            switched_at = it
+        for name in names:
+            torch.testing.assert_close(net.view(name), ref[name].data, rtol=2e-5, atol=2e-6,
+                                       msg=lambda m, name=name, it=it: 'step {} {}: {}'.format(it, name, m))
+    assert switched_at == 2      # the first minibatch without a_c
