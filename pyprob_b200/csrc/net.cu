@@ -806,6 +806,120 @@ __global__ void __launch_bounds__(128) k_smp_bwd_seg(const float* __restrict__ d
   }
 }
 
+// ONE pass over dgates for everything that reduces it over rows (T = 50, B = 512: dgates is 210 MB; the three kernels it
+// replaces — k_step_colsum, k_smp_bwd(_seg), k_wsmp_grad — each streamed it again):
+//   d_pstep[st, col]        += sum over the rows of segment st of dgates[row, col]                 (atomics; zeroed before)
+//   dW_ih[col, E + j]       += sum_rows dgates[row, col] * smp_emb[row, j]
+//   d_smp[row, j]            = sum_col dgates[row, col] * W_ih[col, E + j]  -> ReLU mask -> the previous address's
+//                              sample-embedding layer gradients (shared-memory accumulation per block, see k_smp_bwd_seg)
+// A block owns a slab of rows of one (step, sub-batch) segment; a thread owns NC = 4H / 256 columns.
+constexpr int kRedSlab = 64;
+template <int NC>
+__global__ void __launch_bounds__(256) k_dgates_reduce(const float* __restrict__ dgates, const float* __restrict__ w_smp_t,
+                                                        const float* __restrict__ smp_emb, const float* __restrict__ values,
+                                                        const int* __restrict__ step_prev, const int* __restrict__ step_row0,
+                                                        const int* __restrict__ step_nrows, const int* __restrict__ row_prev,
+                                                        const ppb_addr_desc* __restrict__ addrs, int H4, int S, int I, int E,
+                                                        float* __restrict__ d_pstep, float* __restrict__ grad,
+                                                        int64_t w_ih_off) {
+  __shared__ float s_emb[kRedSlab][8];
+  __shared__ float s_dot[kRedSlab][8];
+  __shared__ float acc_b[8];
+  __shared__ float acc_w[8][heads::CMAX];
+  const int st = blockIdx.y;
+  const int seg0 = step_row0[st], r0 = seg0 + blockIdx.x * kRedSlab;
+  int r1 = r0 + kRedSlab;
+  if (r1 > seg0 + step_nrows[st]) r1 = seg0 + step_nrows[st];
+  if (r0 >= r1) return;
+  const int pa = step_prev[st];
+  const bool smp = pa >= 0;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (smp) {
+    for (int i = tid; i < kRedSlab * 8; i += 256) {
+      const int rr = i >> 3, j = i & 7;
+      s_emb[rr][j] = (r0 + rr < r1 && j < S) ? smp_emb[(int64_t)(r0 + rr) * S + j] : 0.0f;
+      s_dot[rr][j] = 0.0f;
+    }
+    for (int i = tid; i < 8 * heads::CMAX; i += 256) (&acc_w[0][0])[i] = 0.0f;
+    if (tid < 8) acc_b[tid] = 0.0f;
+  }
+  __syncthreads();
+  float colsum[NC], w[NC][4], wg[NC][4];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    colsum[i] = 0.0f;
+    const int col = tid + 256 * i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      w[i][j] = (smp && j < S && col < H4) ? __ldg(w_smp_t + (int64_t)j * H4 + col) : 0.0f;
+      wg[i][j] = 0.0f;
+    }
+  }
+  for (int r = r0; r < r1; ++r) {
+    const int rr = r - r0;
+    float d[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int col = tid + 256 * i;
+      d[i] = col < H4 ? __ldg(dgates + (int64_t)r * H4 + col) : 0.0f;
+      colsum[i] += d[i];
+    }
+    if (smp) {
+      float p[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float e = s_emb[rr][j];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+          wg[i][j] = fmaf(d[i], e, wg[i][j]);
+          p[j] = fmaf(d[i], w[i][j], p[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float t = ppb_warp_sum(p[j]);
+        if (lane == 0 && j < S) atomicAdd(&s_dot[rr][j], t);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int col = tid + 256 * i;
+    if (col < H4) {
+      if (colsum[i] != 0.0f) atomicAdd(d_pstep + (int64_t)st * H4 + col, colsum[i]);
+      if (smp) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < S && wg[i][j] != 0.0f) atomicAdd(grad + w_ih_off + (int64_t)col * I + E + j, wg[i][j]);
+      }
+    }
+  }
+  if (!smp) return;
+  __syncthreads();
+  const ppb_addr_desc a = addrs[pa];
+  const bool is_cat = a.family == PPB_FAMILY_CATEGORICAL;
+  if (tid < r1 - r0) {
+    const float x = values[row_prev[r0 + tid]];
+    const int cidx = (int)x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float sj = s_dot[tid][j];
+      if (j < S && s_emb[tid][j] > 0.0f && sj != 0.0f) {
+        atomicAdd(&acc_b[j], sj);
+        if (is_cat) { if (cidx >= 0 && cidx < a.smp_in) atomicAdd(&acc_w[j][cidx], sj); }
+        else atomicAdd(&acc_w[j][0], sj * x);
+      }
+    }
+  }
+  __syncthreads();
+  const int width = is_cat ? a.smp_in : 1;
+  for (int i = tid; i < S * (width + 1); i += 256) {
+    const int j = i / (width + 1), c = i % (width + 1);
+    if (c == width) { if (acc_b[j] != 0.0f) atomicAdd(grad + a.smp_b_off + j, acc_b[j]); }
+    else if (acc_w[j][c] != 0.0f) atomicAdd(grad + a.smp_w_off + (int64_t)j * a.smp_in + c, acc_w[j][c]);
+  }
+}
+
 // dW_ih[:, E + j] += sum_rows dgates[row, col] * smp_emb[row, j]
 __global__ void k_wsmp_grad(const float* __restrict__ dgates, const float* __restrict__ smp_emb, int R, int H4, int S,
                             int I, int E, float* __restrict__ dw_ih, int rows_per_block) {

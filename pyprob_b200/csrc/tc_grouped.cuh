@@ -251,27 +251,42 @@ __global__ void __launch_bounds__(kThreads, 1) k_grouped(const Problem* __restri
       const int64_t span0 = ((orow0 >> 7) * o_kb + (ocb0 + cb)) * kTileFloats + (orow0 & 127) * 32;
       float* cp = c_p ? c_p + (int64_t)m_base * ldc + n : nullptr;
       const bool c_ok = cp != nullptr && col_ok;
+      // rows in batches of eight: the ReLU-mask loads of a batch are issued together (one L2 round trip per batch instead of
+      // one per row — the mask read used to serialise the whole epilogue: 10 us for a one-chunk GEMM)
 #pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        float x = stg[r][lane] + bias;
-        x = do_relu ? fmaxf(x, 0.0f) : x;
-        const bool live = r < rows;                        // row exists in C
-        x = (col_ok && r < valid_rows) ? x : 0.0f;
-        if (EPI == 0) {
-          if (live && c_ok) st_global(cp + (int64_t)r * ldc, x);
-        } else if (EPI == 1) {
-          if (live && c_ok && x != 0.0f) red_add_global(cp + (int64_t)r * ldc, x);
-        } else {
-          const int64_t pos_k = span0 + r * 32 + ((((lane >> 2) ^ (r & 7))) << 2) + (lane & 3);
-          if (do_mask && live) x = (ld_global(mask_p + pos_k) > 0.0f) ? x : 0.0f;
-          if (live && c_ok) st_global(cp + (int64_t)r * ldc, x);
-          float h, l;
-          split_tf32(x, h, l);
-          if (live && ok_hi) { st_global(ok_hi + pos_k, h); st_global(ok_lo + pos_k, l); }
-          if (live && omn_hi) {
-            const int64_t pos_mn = span0 + r * 32 + ((((lane >> 3) ^ (r & 3))) << 3) + (lane & 7);
-            st_global(omn_hi + pos_mn, h);
-            st_global(omn_lo + pos_mn, l);
+      for (int rb = 0; rb < 32; rb += 8) {
+        float mk[8];
+        if (EPI == 2) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int r = rb + j;
+            const int64_t pos_k = span0 + r * 32 + ((((lane >> 2) ^ (r & 7))) << 2) + (lane & 3);
+            mk[j] = (do_mask && r < rows) ? __ldg(mask_p + pos_k) : 1.0f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = rb + j;
+          float x = stg[r][lane] + bias;
+          x = do_relu ? fmaxf(x, 0.0f) : x;
+          const bool live = r < rows;                        // row exists in C
+          x = (col_ok && r < valid_rows) ? x : 0.0f;
+          if (EPI == 0) {
+            if (live && c_ok) st_global(cp + (int64_t)r * ldc, x);
+          } else if (EPI == 1) {
+            if (live && c_ok && x != 0.0f) red_add_global(cp + (int64_t)r * ldc, x);
+          } else {
+            const int64_t pos_k = span0 + r * 32 + ((((lane >> 2) ^ (r & 7))) << 2) + (lane & 3);
+            if (do_mask && live) x = (mk[j] > 0.0f) ? x : 0.0f;
+            if (live && c_ok) st_global(cp + (int64_t)r * ldc, x);
+            float h, l;
+            split_tf32(x, h, l);
+            if (live && ok_hi) { st_global(ok_hi + pos_k, h); st_global(ok_lo + pos_k, l); }
+            if (live && omn_hi) {
+              const int64_t pos_mn = span0 + r * 32 + ((((lane >> 3) ^ (r & 3))) << 3) + (lane & 7);
+              st_global(omn_hi + pos_mn, h);
+              st_global(omn_lo + pos_mn, l);
+            }
           }
         }
       }

@@ -594,7 +594,7 @@ class InferenceNetworkLSTM(nn.Module):
         segment-aware step (csrc/optim.cu) with the per-tensor step counts the history implies — no difference to the
         reference is ever applied."""
         if (self._seg is not None or self._optimizer_type != Optimizer.ADAM or self._peer is not None
-                or self._last_enc is None or parallel.world_info()[0] > 1):
+                or self._last_enc is None or parallel.world_info()[0] > 1 or os.environ.get('PPB_FLAT_ADAM') == '1'):
             return
         present = self._segment_presence(self._last_enc, force=True)
         sig = present.tobytes()

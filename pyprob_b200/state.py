@@ -28,8 +28,11 @@ _network = None
 _previous_site = None
 _observed = {}
 _mask = None            # bool [n] of lanes executing the current statement, None = all
+_mask_idx = None        # indices of the lanes of _mask (computed once per while_loop iteration), or None
+_mask_parent = None     # the mask this one was narrowed from (while_loop: the previous iteration's mask)
 _trace_start = None
 _target_cache = {}
+_NO_MASK_YET = object()
 
 
 # ---- addressing (same information content as the reference's bytecode addresses, state.py:31-84) --------
@@ -219,11 +222,20 @@ def _sample_from_proposal(trace, distribution, addr, n):
     known = addr in net._addresses
     if not known:
         warnings.warn('Address unknown by inference network: {}'.format(addr))
-    idx = None if _mask is None else torch.nonzero(_mask).view(-1)
+    idx = None if _mask is None else (_mask_idx if _mask_idx is not None else torch.nonzero(_mask).view(-1))
+    if idx is not None and idx.numel() == 0:     # nobody executes the statement: nothing to propose, nothing to weigh
+        return distribution.sample(n)
     p0, p1 = _prior_params(distribution)
-    # group the executing lanes by the site they came from
+    # group the executing lanes by the site they came from.  Known on the host without a device round trip when every lane
+    # shares its previous site, or when this mask is (a narrowing of) the mask of the previous proposal site: then all of its
+    # lanes executed that site last.
+    last_mask = st.get('last_mask', _NO_MASK_YET)
     if idx is None and st['uniform_prev'] is not None:
         groups = [(st['uniform_prev'], None)]
+    elif idx is not None and st['uniform_prev'] is not None:
+        groups = [(st['uniform_prev'], None)]
+    elif idx is not None and last_mask is not _NO_MASK_YET and (_mask is last_mask or _mask_parent is last_mask):
+        groups = [(st['last_id'], None)]
     else:
         ids = st['prev_id'] if idx is None else st['prev_id'][idx]
         uniq = torch.unique(ids).tolist()
@@ -296,6 +308,7 @@ def _sample_from_proposal(trace, distribution, addr, n):
         st['prev_id'].index_fill_(0, idx, new_id)
         st['prev_value'].index_copy_(0, idx, value.to(torch.float32)[idx])
         st['uniform_prev'] = None
+    st['last_mask'], st['last_id'] = _mask, new_id
     return value
 
 
@@ -321,23 +334,28 @@ def while_loop(cond_fn, body_fn, state, max_iterations=10000):
 
     ``state`` is a dict of length-n tensors; ``cond_fn(state)`` returns a bool [n]; lanes whose condition is
     false stop executing sample/observe statements (their trace ends there) while the others continue."""
-    global _mask
+    global _mask, _mask_idx, _mask_parent
     trace = _current_trace
     n = trace.n if trace is not None else None
-    outer = _mask
+    outer, outer_idx, outer_parent = _mask, _mask_idx, _mask_parent
     state = {k: (v if torch.is_tensor(v) else torch.full((n,), float(v), device='cuda')) for k, v in state.items()}
+    prev = None
     for _ in range(max_iterations):
         m = cond_fn(state)
         if outer is not None:
             m = m & outer
-        if not bool(m.any()):
+        if prev is not None:
+            m = m & prev          # a lane that left the loop stays out (its state is frozen, so cond cannot change anyway)
+        idx = torch.nonzero(m).view(-1)     # the one device round trip of the iteration: who is still in
+        if idx.numel() == 0:
             break
-        _mask = m
+        _mask, _mask_idx, _mask_parent = m, idx, (prev if prev is not None else outer)
         try:
             out = body_fn(state)
         finally:
-            _mask = outer
+            _mask, _mask_idx, _mask_parent = outer, outer_idx, outer_parent
         state = {k: torch.where(m, out[k].to(state[k].dtype), state[k]) for k in state}
+        prev = m
     else:
         raise RuntimeError('while_loop: exceeded max_iterations')
     return state

@@ -103,22 +103,47 @@ def test_loss_and_grads_vs_oracle_random(cuda, seed, lstm_dim, K, spec, precisio
 
 
 def test_adam_step_vs_torch(cuda):
+    """Optimizer.ADAM against torch.optim.Adam over the reference's parameter tensors, with .grad = None for the tensors the
+    minibatch does not touch (GUM: the sample-embedding layer of its only address is never an input) — torch skips those:
+    no weight decay, no moment update (inference_network.py:343-355 on torch >= 2.0)."""
     fx = netfixture.load('gum')
     net = _net_from_fixture(fx)
     batch = synthetic.ArrayBatch(_subs_numpy(fx['subs']))
     from pyprob_b200.util import Optimizer
     net._optimizer_type, net._learning_rate_init, net._weight_decay = Optimizer.ADAM, 1e-3, 1e-2
     net._create_optimizer()
-    ref_p = net._arena.data.clone().requires_grad_(True)
-    opt = torch.optim.Adam([ref_p], lr=1e-3, weight_decay=1e-2)
+    names = net._segment_names()
+    ref = {k: net.view(k).clone().requires_grad_(True) for k in names}
+    opt = torch.optim.Adam([ref[k] for k in names], lr=1e-3, weight_decay=1e-2)
     for _ in range(3):
         net._arena.grad = None
         ok, loss = net._loss(batch)
         loss.backward()
-        ref_p.grad = net._arena.grad.clone()
+        present = net._segment_presence(net._last_enc, force=True)
+        assert not present.all()
+        for k, name in enumerate(names):
+            ref[name].grad = net.grad_view(name).clone() if present[k] else None
         opt.step()
         net.optimizer_step()
-    torch.testing.assert_close(net._arena.data, ref_p.data, rtol=1e-5, atol=1e-6)
+    for name in names:
+        torch.testing.assert_close(net.view(name), ref[name].data, rtol=1e-5, atol=1e-6, msg=lambda m, name=name: name + ': ' + m)
+
+
+def test_flat_adam_kernel_vs_torch_on_the_whole_arena(cuda):
+    """The flat kernel itself (ppb_adam_step): every element updated, as torch.optim.Adam on one tensor."""
+    from pyprob_b200._lib import call, ptr, stream
+    gen = torch.Generator().manual_seed(0)
+    n = 100003
+    p = torch.randn(n, generator=gen).to(cuda)
+    ref_p = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref_p], lr=1e-3, weight_decay=1e-2)
+    m, v = torch.zeros(n, device=cuda), torch.zeros(n, device=cuda)
+    for step in range(1, 4):
+        g = torch.randn(n, generator=gen).to(cuda)
+        ref_p.grad = g.clone()
+        opt.step()
+        call('ppb_adam_step', ptr(p), ptr(g), ptr(m), ptr(v), n, 1e-3, 0.9, 0.999, 1e-8, 1e-2, step, 1.0, stream())
+    torch.testing.assert_close(p, ref_p.data, rtol=1e-5, atol=1e-6)
 
 
 def test_loss_is_additive_over_sub_batches_and_grad_scales(cuda):
