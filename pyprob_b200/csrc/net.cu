@@ -49,6 +49,10 @@ struct ppb_net {
   int pack_tiles = 0;
   WImg w_ihE, w_hh;
   std::vector<WImg> w1, w2;
+  // wide observe-embedding layers on the tensor cores (layers >= 1 of every observable chain, the final chain)
+  WImg w_obs[PPB_MAX_OBS][PPB_MAX_FF_LAYERS];
+  WImg w_fin[PPB_MAX_FF_LAYERS];
+  int obs_tc = 0;
   // content hashes of the problem lists last uploaded to each device region: identical lists are not re-sent,
   // which also makes a repeated step capturable in a CUDA graph (no host->device copy inside the capture)
   uint64_t slot_hash[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};

@@ -305,21 +305,31 @@ __global__ void __launch_bounds__(tcg::kThreads, 1) k_lstm_cluster(const tcl::St
 #pragma unroll
       for (int s = 0; s < 8; ++s) wsmp[g][s] = (s < S) ? __ldg(io.w_smp_t + (int64_t)s * H4 + g * H + u) : 0.0f;
     const int64_t hkb = io.hkb;
+    // row metadata of all this warp's rows first: it heads every row's dependency chain
+    int m_tr[kRowsPerWarp], m_st[kRowsPerWarp];
+    int64_t m_rp[kRowsPerWarp];
+#pragma unroll
+    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+      const int64_t row = (int64_t)P.row0 + mt * 128 + split * kRowsPerCta + ew * kRowsPerWarp + rr;
+      m_tr[rr] = __ldg(io.row_trace + row);
+      m_st[rr] = __ldg(io.row_step + row);
+      m_rp[rr] = __ldg(io.row_prev + row);
+    }
 #pragma unroll
     for (int rr = 0; rr < kRowsPerWarp; ++rr) {
       const int trow = split * kRowsPerCta + ew * kRowsPerWarp + rr;
       const int64_t row = (int64_t)P.row0 + mt * 128 + trow;     // global row of the step
-      const int tr = __ldg(io.row_trace + row);
+      const int tr = m_tr[rr];
       float act[4] = {0.f, 0.f, 0.f, 0.f}, cn = 0.0f, hn = 0.0f;
       if (tr >= 0) {   // warp-uniform
         float v[4];
         reduce_row<CS>(sm, trow, lane, v);
-        const int st = __ldg(io.row_step + row);
-        const int64_t rp = __ldg(io.row_prev + row);
+        const int st = m_st[rr];
+        const int64_t rp = m_rp[rr] < 0 ? 0 : m_rp[rr];
         float sm_e[8];
 #pragma unroll
         for (int s = 0; s < 8; ++s) sm_e[s] = (s < S) ? __ldg(io.smp_emb + row * S + s) : 0.0f;
-        const float cp = tcg::ld_global(io.c + rp * H + u);
+        const float cp = __ldcg(io.c + rp * H + u);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int col = g * H + u;
@@ -411,21 +421,28 @@ __global__ void __launch_bounds__(tcg::kThreads, 1) k_lstm_bwd_cluster(const BSt
         if (u - lane >= H) continue;   // warp-uniform: unit block beyond H (H < 128 * tiles_n)
         float d[4] = {0.f, 0.f, 0.f, 0.f};
         if (tr >= 0) {
+          // every operand of this (row, unit) in flight at once: plain (non-volatile) loads, one L2 round trip — the
+          // read-modify-write of d_pobs used to be four dependent round trips per unit
           const float* gr = io.gates + row * H4;
+          float* dp = io.d_pobs + (int64_t)tr * H4;
           const float ig = __ldg(gr + u), fg = __ldg(gr + H + u), gg = __ldg(gr + 2 * H + u), og = __ldg(gr + 3 * H + u);
           const float cn = __ldg(io.c + row * H + u);
           const float cp = (P.t > 0) ? __ldg(io.c + rp * H + u) : 0.0f;
+          const float dh_head = __ldg(io.dh + row * H + u);
+          const float dc_next = __ldcg(io.dc + nx * H + u);
+          float old[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) old[q] = __ldcg(dp + q * H + u);
           const float tc = tanhf(cn);
-          const float dht = __ldg(io.dh + row * H + u) + v[g];
-          const float dct = tcg::ld_global(io.dc + nx * H + u) + dht * og * (1.0f - tc * tc);
+          const float dht = dh_head + v[g];
+          const float dct = dc_next + dht * og * (1.0f - tc * tc);
           d[0] = dct * gg * ig * (1.0f - ig);
           d[1] = dct * cp * fg * (1.0f - fg);
           d[2] = dct * ig * (1.0f - gg * gg);
           d[3] = dht * tc * og * (1.0f - og);
           tcg::st_global(io.dc + row * H + u, dct * fg);
-          float* dp = io.d_pobs + (int64_t)tr * H4;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) tcg::st_global(dp + q * H + u, tcg::ld_global(dp + q * H + u) + d[q]);
+          for (int q = 0; q < 4; ++q) tcg::st_global(dp + q * H + u, old[q] + d[q]);
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
