@@ -88,6 +88,16 @@ struct ppb_net {
   int fork_next = 0;
   int single_stream = 0;            // PPB_SINGLE_STREAM=1: everything on the caller's stream (A/B, debugging)
   int pack_tiles_no_hh = 0;         // weight-image tiles without W_hh (a T = 1 step never reads it)
+  // ppb_ic_train_step_host: the whole step cached as an instantiated CUDA graph per batch structure
+  int host_graph = 0;               // PPB_HOST_STEP_GRAPH=1
+  cudaStream_t host_stream = nullptr;
+  cudaGraphExec_t host_exec = nullptr;
+  uint64_t host_key = 0;
+  int host_seen = 0;
+  float* host_hyper_dev = nullptr;  // [6] lr, b1, b2, eps, wd, grad_scale
+  void* host_state_dev = nullptr;   // 16 B Adam state (ppb_adam_step_dev)
+  float host_hyper[6] = {0, 0, 0, 0, 0, 0};
+  int64_t host_step_dev = -1;       // value of the device step counter
   // pinned staging ring for problem lists
   Problem* h_stage[2] = {nullptr, nullptr};
   cudaEvent_t ev_stage[2] = {nullptr, nullptr};
@@ -1044,6 +1054,8 @@ int ppb_net_create(ppb_net** out, const ppb_net_desc* d) {
   n->fused_cell = (fc && fc[0] >= '0' && fc[0] <= '3') ? fc[0] - '0' : 3;
   const char* fb = getenv("PPB_FUSED_CELL_BWD");
   n->fused_cell_bwd = (fb && fb[0] == '0') ? 0 : 1;
+  const char* hg = getenv("PPB_HOST_STEP_GRAPH");
+  n->host_graph = (hg && hg[0] == '1') ? 1 : 0;
   const char* ss = getenv("PPB_SINGLE_STREAM");
   n->single_stream = (ss && ss[0] == '1') ? 1 : 0;
   // created up front: a training step must be capturable in a CUDA graph right after its first eager run
@@ -1098,6 +1110,10 @@ int ppb_net_destroy(ppb_net* net) {
   if (net->d_lstm_steps) cudaFree(net->d_lstm_steps);
   if (net->d_lstm_progress) cudaFree(net->d_lstm_progress);
   if (net->d_bsteps) cudaFree(net->d_bsteps);
+  if (net->host_exec) cudaGraphExecDestroy(net->host_exec);
+  if (net->host_stream) cudaStreamDestroy(net->host_stream);
+  if (net->host_hyper_dev) cudaFree(net->host_hyper_dev);
+  if (net->host_state_dev) cudaFree(net->host_state_dev);
   delete net;
   return PPB_OK;
 }
@@ -1856,7 +1872,6 @@ int ppb_ic_train_step_host(ppb_net* net, float* arena, float* grad_arena, float*
   PPB_CHECK_ARG(net && arena && grad_arena && exp_avg && exp_avg_sq && batch_image_host && batch_image_dev && workspace,
                 "null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  PPB_CUDA(cudaMemcpyAsync(batch_image_dev, batch_image_host, batch_image_bytes, cudaMemcpyHostToDevice, st));
   ppb_batch b;
   int rc = ppb_batch_from_image(batch_image_host, batch_image_dev, batch_image_bytes, &b);
   if (rc) return rc;
@@ -1865,17 +1880,106 @@ int ppb_ic_train_step_host(ppb_net* net, float* arena, float* grad_arena, float*
   PPB_CHECK_ARG(workspace_bytes >= need + 256, "workspace too small (need ppb_ic_workspace_bytes + 256)");
   float* loss_dev = (float*)((char*)workspace + need);  // loss scalar + status live after the carved region
   int32_t* status_dev = (int32_t*)(loss_dev + 1);
-  PPB_CUDA(cudaMemsetAsync(grad_arena, 0, arena_floats * sizeof(float), st));
-  rc = ppb_ic_loss_forward(net, arena, &b, workspace, need, precision, loss_dev, status_dev, nullptr, 1, stream);
+
+  if (!net->host_graph || g_prof.on) {
+    PPB_CUDA(cudaMemcpyAsync(batch_image_dev, batch_image_host, batch_image_bytes, cudaMemcpyHostToDevice, st));
+    PPB_CUDA(cudaMemsetAsync(grad_arena, 0, arena_floats * sizeof(float), st));
+    rc = ppb_ic_loss_forward(net, arena, &b, workspace, need, precision, loss_dev, status_dev, nullptr, 1, stream);
+    if (rc) return rc;
+    rc = ppb_ic_loss_backward(net, arena, grad_arena, &b, workspace, need, precision, 1.0f, stream);
+    if (rc) return rc;
+    rc = ppb_adam_step(arena, grad_arena, exp_avg, exp_avg_sq, arena_floats, lr, beta1, beta2, eps, weight_decay, step, 1.0f,
+                       stream);
+    if (rc) return rc;
+    if (loss_host) PPB_CUDA(cudaMemcpyAsync(loss_host, loss_dev, sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (status_host) PPB_CUDA(cudaMemcpyAsync(status_host, status_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PPB_CUDA(cudaStreamSynchronize(st));
+    return PPB_OK;
+  }
+
+  // ---- graph-cached variant: the launches of a step depend only on the batch STRUCTURE (host index arrays) and on the
+  // buffers; the first call with a structure runs eagerly (and uploads the problem lists), the second captures the step
+  // into a graph on an internal stream, later calls replay it.  Adam's step count and hyper-parameters live in device memory.
+  if (!net->host_stream) {
+    PPB_CUDA(cudaStreamCreateWithFlags(&net->host_stream, cudaStreamNonBlocking));
+    PPB_CUDA(cudaMalloc((void**)&net->host_hyper_dev, 6 * sizeof(float)));
+    PPB_CUDA(cudaMalloc(&net->host_state_dev, 16));
+    PPB_CUDA(cudaMemset(net->host_state_dev, 0, 16));
+    net->host_step_dev = 0;
+  }
+  cudaStream_t hs = net->host_stream;
+  uint64_t key = fnv1a(&d, sizeof(d));
+  key = fnv1a(b.row_off_host, sizeof(int32_t) * (d.T + 1), key);
+  key = fnv1a(b.group_addr_host, sizeof(int32_t) * d.G, key);
+  key = fnv1a(b.group_start_host, sizeof(int32_t) * (d.G + 1), key);
+  key = fnv1a(b.step_addr_host, sizeof(int32_t) * d.NS, key);
+  key = fnv1a(b.step_row0_host, sizeof(int32_t) * d.NS, key);
+  key = fnv1a(b.step_nrows_host, sizeof(int32_t) * d.NS, key);
+  key = fnv1a(b.step_t_host, sizeof(int32_t) * d.NS, key);
+  key = fnv1a(b.step_prev_row0_host, sizeof(int32_t) * d.NS, key);
+  const void* ptrs[8] = {arena, grad_arena, exp_avg, exp_avg_sq, batch_image_dev, workspace, (const void*)(intptr_t)precision,
+                         (const void*)(intptr_t)arena_floats};
+  key = fnv1a(ptrs, sizeof(ptrs), key);
+  key = fnv1a(&net->arena_floats, sizeof(net->arena_floats), key);
+  if (key != net->host_key) {
+    if (net->host_exec) { cudaGraphExecDestroy(net->host_exec); net->host_exec = nullptr; }
+    net->host_key = key;
+    net->host_seen = 0;
+  }
+  // order after whatever the caller queued on its stream
+  rc = stream_after(net, st, hs);
   if (rc) return rc;
-  rc = ppb_ic_loss_backward(net, arena, grad_arena, &b, workspace, need, precision, 1.0f, stream);
-  if (rc) return rc;
-  rc = ppb_adam_step(arena, grad_arena, exp_avg, exp_avg_sq, arena_floats, lr, beta1, beta2, eps, weight_decay, step, 1.0f,
-                     stream);
-  if (rc) return rc;
-  if (loss_host) PPB_CUDA(cudaMemcpyAsync(loss_host, loss_dev, sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (status_host) PPB_CUDA(cudaMemcpyAsync(status_host, status_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  PPB_CUDA(cudaStreamSynchronize(st));
+  PPB_CUDA(cudaMemcpyAsync(batch_image_dev, batch_image_host, batch_image_bytes, cudaMemcpyHostToDevice, hs));
+  const float hyper[6] = {lr, beta1, beta2, eps, weight_decay, 1.0f};
+  if (memcmp(hyper, net->host_hyper, sizeof(hyper)) != 0) {
+    memcpy(net->host_hyper, hyper, sizeof(hyper));
+    PPB_CUDA(cudaMemcpyAsync(net->host_hyper_dev, net->host_hyper, sizeof(hyper), cudaMemcpyHostToDevice, hs));
+  }
+  if (net->host_step_dev != step - 1) {
+    const int64_t prev = step - 1;
+    PPB_CUDA(cudaMemcpyAsync(net->host_state_dev, &prev, sizeof(prev), cudaMemcpyHostToDevice, hs));
+    PPB_CUDA(cudaStreamSynchronize(hs));   // `prev` lives on this frame
+  }
+  auto enqueue = [&](cudaStream_t q) -> int {
+    PPB_CUDA(cudaMemsetAsync(grad_arena, 0, arena_floats * sizeof(float), q));
+    int r = ppb_ic_loss_forward(net, arena, &b, workspace, need, precision, loss_dev, status_dev, nullptr, 1, (void*)q);
+    if (r) return r;
+    r = ppb_ic_loss_backward(net, arena, grad_arena, &b, workspace, need, precision, 1.0f, (void*)q);
+    if (r) return r;
+    return ppb_adam_step_dev(arena, grad_arena, exp_avg, exp_avg_sq, arena_floats, net->host_hyper_dev, net->host_state_dev,
+                             (void*)q);
+  };
+  if (net->host_exec) {
+    PPB_CUDA(cudaGraphLaunch(net->host_exec, hs));
+  } else if (net->host_seen >= 1) {
+    cudaGraph_t graph = nullptr;
+    PPB_CUDA(cudaStreamBeginCapture(hs, cudaStreamCaptureModeThreadLocal));
+    rc = enqueue(hs);
+    cudaError_t ce = cudaStreamEndCapture(hs, &graph);
+    if (rc || ce != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      if (rc) return rc;
+      ppb_set_error("ppb_ic_train_step_host: graph capture failed: %s", cudaGetErrorString(ce));
+      return (int)ce;
+    }
+    ce = cudaGraphInstantiate(&net->host_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) {
+      net->host_exec = nullptr;
+      ppb_set_error("ppb_ic_train_step_host: cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+      return (int)ce;
+    }
+    PPB_CUDA(cudaGraphLaunch(net->host_exec, hs));
+  } else {
+    rc = enqueue(hs);
+    if (rc) return rc;
+  }
+  net->host_seen += 1;
+  net->host_step_dev = step;
+  if (loss_host) PPB_CUDA(cudaMemcpyAsync(loss_host, loss_dev, sizeof(float), cudaMemcpyDeviceToHost, hs));
+  if (status_host) PPB_CUDA(cudaMemcpyAsync(status_host, status_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, hs));
+  PPB_CUDA(cudaStreamSynchronize(hs));
   return PPB_OK;
 }
 

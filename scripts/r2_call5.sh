@@ -9,3 +9,7 @@ for cfg in "A_default" "B_single PPB_SINGLE_STREAM=1" "C_nofusedbwd PPB_FUSED_CE
   env "$@" timeout 100 python scripts/profile_step.py 0 s50 512 > gpurun_out/r2c5_prof_$name.txt 2>&1
   echo "== $name: $(head -1 gpurun_out/r2c5_prof_$name.txt)"; sed -n 4,11p gpurun_out/r2c5_prof_$name.txt | cut -c1-130
 done
+PPB_HOST_STEP_GRAPH=1 timeout 200 python bench.py --no-extra --cpu-budget 1 > gpurun_out/r2c5_bench_hostgraph.json 2> gpurun_out/r2c5_bench_hostgraph.err
+echo "== host graph =="; python -c "
+import json;d=json.load(open('gpurun_out/r2c5_bench_hostgraph.json'));print(d['ms_per_step'], d['e2e'])"; tail -2 gpurun_out/r2c5_bench_hostgraph.err
+PPB_HOST_STEP_GRAPH=1 timeout 200 python -m pytest tests/test_host_step_gpu.py -m gpu -q 2>&1 | tail -5

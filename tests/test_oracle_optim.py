@@ -78,3 +78,43 @@ def test_segment_presence_matches_autograd_none_pattern():
     assert checked_absent > 0   # the single-sub-batch cases really leave some tensors without a gradient
     net._skip_absent_gradients = False
     assert net._segment_presence(enc).min() == 1
+
+
+def test_flat_adam_hands_over_to_the_skipping_step_at_the_right_moment(monkeypatch):
+    """Host logic of Optimizer.ADAM (network._maybe_switch_to_segmented): the flat kernel is kept exactly as long as it is
+    indistinguishable from torch.optim's skipping of grad-None tensors — constant set of untouched tensors AND zero weight
+    decay — and the hand-over initialises every tensor's step count with what the history implies."""
+    import torch
+    from pyprob_b200.network import InferenceNetworkLSTM
+    from pyprob_b200.util import Optimizer
+    names = ['a', 'b', 'c', 'd']
+
+    def make(weight_decay):
+        net = InferenceNetworkLSTM(model=None, observe_embeddings={'o': {}})
+        net._optimizer_type, net._weight_decay, net._last_enc = Optimizer.ADAM, weight_decay, object()
+        net._present_sig, net._seg, net._optimizer_step = None, None, 0
+        monkeypatch.setattr(net, '_segment_names', lambda: names)
+
+        def create():
+            net._seg = {'names': names, 'steps': torch.zeros(len(names), dtype=torch.int64)}
+        monkeypatch.setattr(net, '_create_segment_state', create)
+        return net
+
+    def run(net, patterns):
+        switched = None
+        for it, pat in enumerate(patterns):
+            monkeypatch.setattr(net, '_segment_presence', lambda enc, force=False, pat=pat: np.asarray(pat, dtype=np.int32))
+            net._maybe_switch_to_segmented()
+            if net._seg is not None and switched is None:
+                switched = (it, net._seg['steps'].tolist())
+            net._optimizer_step += 1
+        return switched
+
+    # constant pattern, no weight decay: never switches, even though tensor d is never touched
+    assert run(make(0.0), [[1, 1, 1, 0]] * 5) is None
+    # pattern changes at step 3 (0-based): tensors touched so far took 3 steps, the never-touched one none
+    assert run(make(0.0), [[1, 1, 1, 0]] * 3 + [[1, 0, 1, 0], [1, 1, 1, 1]]) == (3, [3, 3, 3, 0])
+    # weight decay with an untouched tensor: the flat kernel would decay it, torch would not -> switch before step 1
+    assert run(make(1e-2), [[1, 1, 1, 0]] * 2) == (0, [0, 0, 0, 0])
+    # weight decay but everything touched: no switch
+    assert run(make(1e-2), [[1, 1, 1, 1]] * 3) is None
