@@ -131,6 +131,9 @@ class InferenceNetworkLSTM(nn.Module):
         self._peer = None                 # parallel.PeerAdam when training data-parallel over NVLink
         self._seg = None                  # device tables of the segment-aware optimiser step (LARC / SGD / skipping)
         self._skip_absent_gradients = False   # True: tensors absent from a minibatch are skipped like .grad None
+        # Optimizer.ADAM hands over to the skipping step by itself when the flat kernel would differ from torch.optim
+        # (_maybe_switch_to_segmented); PPB_FLAT_ADAM=1 keeps the flat kernel (absent gradient = zeros) throughout
+        self._auto_skip_absent = os.environ.get('PPB_FLAT_ADAM') != '1'
         self._last_enc = None
         self._learning_rate_init = None
         self._learning_rate_end = None
@@ -594,7 +597,7 @@ class InferenceNetworkLSTM(nn.Module):
         segment-aware step (csrc/optim.cu) with the per-tensor step counts the history implies — no difference to the
         reference is ever applied."""
         if (self._seg is not None or self._optimizer_type != Optimizer.ADAM or self._peer is not None
-                or self._last_enc is None or parallel.world_info()[0] > 1 or os.environ.get('PPB_FLAT_ADAM') == '1'):
+                or self._last_enc is None or parallel.world_info()[0] > 1 or not self._auto_skip_absent):
             return
         present = self._segment_presence(self._last_enc, force=True)
         sig = present.tobytes()
@@ -871,7 +874,8 @@ class InferenceNetworkLSTM(nn.Module):
         ret._arena = nn.Parameter(ret._arena_store[:ret._arena_used])
         ret._handle = None
         ret._tables_dirty = True
-        for k, default in (('_peer', None), ('_seg', None), ('_skip_absent_gradients', False), ('_last_enc', None)):
+        for k, default in (('_peer', None), ('_seg', None), ('_skip_absent_gradients', False), ('_last_enc', None),
+                           ('_auto_skip_absent', True), ('_present_sig', None)):
             ret.__dict__.setdefault(k, default)   # checkpoints written before these attributes existed
         if data['optimizer_state'] is not None:
             ret._create_optimizer(data['optimizer_state'])

@@ -112,6 +112,7 @@ def test_adam_step_vs_torch(cuda):
     from pyprob_b200.util import Optimizer
     net._optimizer_type, net._learning_rate_init, net._weight_decay = Optimizer.ADAM, 1e-3, 1e-2
     net._create_optimizer()
+    net._auto_skip_absent = True
     names = net._segment_names()
     ref = {k: net.view(k).clone().requires_grad_(True) for k in names}
     opt = torch.optim.Adam([ref[k] for k in names], lr=1e-3, weight_decay=1e-2)

@@ -126,6 +126,7 @@ def test_flat_adam_switches_to_skipping_when_the_present_set_changes(cuda):
     net = synthetic.build_network({'o0': {'dim': 8, 'depth': 2}}, [2], table, lstm_dim=32, mixture_components=3, seed=3)
     net._optimizer_type, net._learning_rate_init, net._weight_decay = Optimizer.ADAM, 1e-3, 0.0
     net._create_optimizer()
+    net._auto_skip_absent = True
     rng = np.random.default_rng(8)
     full = synthetic.ArrayBatch([synthetic.random_sub_batch(rng, table, 20, 2)])
     part = synthetic.ArrayBatch([synthetic.random_sub_batch(rng, table[:2], 12, 2)])

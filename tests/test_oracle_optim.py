@@ -92,7 +92,7 @@ def test_flat_adam_hands_over_to_the_skipping_step_at_the_right_moment(monkeypat
     def make(weight_decay):
         net = InferenceNetworkLSTM(model=None, observe_embeddings={'o': {}})
         net._optimizer_type, net._weight_decay, net._last_enc = Optimizer.ADAM, weight_decay, object()
-        net._present_sig, net._seg, net._optimizer_step = None, None, 0
+        net._present_sig, net._seg, net._optimizer_step, net._auto_skip_absent = None, None, 0, True
         monkeypatch.setattr(net, '_segment_names', lambda: names)
 
         def create():
