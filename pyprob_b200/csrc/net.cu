@@ -650,14 +650,6 @@ __global__ void __launch_bounds__(256) k_head_nll(const float* __restrict__ out_
   }
 }
 
-__global__ void k_publish_loss(const float* __restrict__ loss_acc, float* __restrict__ loss_out,
-                               int* __restrict__ status_out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    if (loss_out) *loss_out = loss_acc[0];
-    if (status_out) *status_out = *reinterpret_cast<const int*>(loss_acc + 1);
-  }
-}
-
 // LSTM cell backward, one time step (reverse order).  dgates rows of this step are produced here;
 // dh_rec = dgates[t+1] W_hh (prefix of this step's rows), dc carries d c_t across steps.
 __global__ void __launch_bounds__(256) k_cell_bwd(const float* __restrict__ gates, const float* __restrict__ c,

@@ -469,8 +469,7 @@ __global__ void __launch_bounds__(tcg::kThreads, 1) k_lstm_bwd_cluster(const BSt
 // host-side launch with a (CS, 1, 1) cluster
 template <typename Kernel, typename... Args>
 inline cudaError_t launch_cluster(Kernel kernel, int grid, int cluster, size_t smem, cudaStream_t st, Args... args) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid, 1, 1);
   cfg.blockDim = dim3(tcg::kThreads, 1, 1);
   cfg.dynamicSmemBytes = smem;
