@@ -134,3 +134,21 @@ def test_offline_dataset_shards_minibatches_over_ranks_world2(tmp_path):
         assert all(size == 16 for size, _ in res[0][2][epoch] + res[1][2][epoch])
         assert not set(a) & set(b)                         # disjoint minibatches
         assert len(set(a)) == len(a) and len(set(b)) == len(b)
+
+
+def test_owned_optimizer_slices_partition_the_arena():
+    """Checkpoint gather under the fused data-parallel step: the slice whose Adam moments live on rank r (network._owned_slice)
+    must be the slice k_dp_adam gives that rank (csrc/dp.cu: ceil(n / 4 world) float4 blocks each) and together they must
+    cover the arena exactly once."""
+    from pyprob_b200.network import InferenceNetworkLSTM
+    net = InferenceNetworkLSTM(model=None, observe_embeddings={'o': {}})
+    for n in (1, 7, 100003, 1643588):
+        for world in (1, 2, 3, 8):
+            per = ((n + world * 4 - 1) // (world * 4)) * 4
+            covered = 0
+            for r in range(world):
+                lo, hi = net._owned_slice(n, world, r)
+                assert lo == min(n, r * per) and hi == min(n, lo + per) and lo % 4 == 0
+                assert lo == covered or lo == n
+                covered = max(covered, hi)
+            assert covered == n
