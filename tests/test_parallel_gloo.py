@@ -148,7 +148,7 @@ def test_owned_optimizer_slices_partition_the_arena():
             covered = 0
             for r in range(world):
                 lo, hi = net._owned_slice(n, world, r)
-                assert lo == min(n, r * per) and hi == min(n, lo + per) and lo % 4 == 0
+                assert lo == min(n, r * per) and hi == min(n, lo + per) and (lo % 4 == 0 or lo == n)
                 assert lo == covered or lo == n
                 covered = max(covered, hi)
             assert covered == n
