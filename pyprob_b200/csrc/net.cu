@@ -1445,8 +1445,14 @@ __global__ void __launch_bounds__(256) k_adam_dev(float* __restrict__ p, const f
   const float step = lr / s_bc[0], bc2_sqrt = s_bc[1];
   const int64_t n4 = vec ? (n >> 2) : 0;
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
-    float4 pp = reinterpret_cast<float4*>(p)[q], gg = reinterpret_cast<const float4*>(g)[q];
+    float4 gg = reinterpret_cast<const float4*>(g)[q];
     float4 mm = reinterpret_cast<float4*>(m)[q], vv = reinterpret_cast<float4*>(v)[q];
+    // a tensor that has never seen a gradient (g = m = v = 0) and no weight decay: the update is exactly zero — skip
+    // the parameter read and all three writes (T = 1 models never touch W_hh: 64 % of the configs[1] arena)
+    if (wd == 0.0f && gg.x == 0.0f && gg.y == 0.0f && gg.z == 0.0f && gg.w == 0.0f && mm.x == 0.0f && mm.y == 0.0f &&
+        mm.z == 0.0f && mm.w == 0.0f && vv.x == 0.0f && vv.y == 0.0f && vv.z == 0.0f && vv.w == 0.0f)
+      continue;
+    float4 pp = reinterpret_cast<float4*>(p)[q];
     ppb_adam_update(pp.x, gg.x, mm.x, vv.x, b1, b2, eps, wd, gscale, step, bc2_sqrt);
     ppb_adam_update(pp.y, gg.y, mm.y, vv.y, b1, b2, eps, wd, gscale, step, bc2_sqrt);
     ppb_adam_update(pp.z, gg.z, mm.z, vv.z, b1, b2, eps, wd, gscale, step, bc2_sqrt);
