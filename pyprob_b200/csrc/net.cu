@@ -89,7 +89,7 @@ struct ppb_net {
   int single_stream = 0;            // PPB_SINGLE_STREAM=1: everything on the caller's stream (A/B, debugging)
   int pack_tiles_no_hh = 0;         // weight-image tiles without W_hh (a T = 1 step never reads it)
   // ppb_ic_train_step_host: the whole step cached as an instantiated CUDA graph per batch structure
-  int host_graph = 0;               // PPB_HOST_STEP_GRAPH=1
+  int host_graph = 1;               // PPB_HOST_STEP_GRAPH=0 disables
   cudaStream_t host_stream = nullptr;
   cudaGraphExec_t host_exec = nullptr;
   uint64_t host_key = 0;
@@ -861,13 +861,20 @@ __global__ void __launch_bounds__(256) k_dgates_reduce(const float* __restrict__
       wg[i][j] = 0.0f;
     }
   }
+  float dn[NC];   // next row's values: two rows of loads in flight (the row loop is latency-bound otherwise)
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int col = tid + 256 * i;
+    dn[i] = col < H4 ? __ldg(dgates + (int64_t)r0 * H4 + col) : 0.0f;
+  }
   for (int r = r0; r < r1; ++r) {
     const int rr = r - r0;
     float d[NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
       const int col = tid + 256 * i;
-      d[i] = col < H4 ? __ldg(dgates + (int64_t)r * H4 + col) : 0.0f;
+      d[i] = dn[i];
+      dn[i] = (r + 1 < r1 && col < H4) ? __ldg(dgates + (int64_t)(r + 1) * H4 + col) : 0.0f;
       colsum[i] += d[i];
     }
     if (smp) {
@@ -1047,7 +1054,7 @@ int ppb_net_create(ppb_net** out, const ppb_net_desc* d) {
   const char* fb = getenv("PPB_FUSED_CELL_BWD");
   n->fused_cell_bwd = (fb && fb[0] == '0') ? 0 : 1;
   const char* hg = getenv("PPB_HOST_STEP_GRAPH");
-  n->host_graph = (hg && hg[0] == '1') ? 1 : 0;
+  n->host_graph = (hg && hg[0] == '0') ? 0 : 1;   // on by default (PPB_HOST_STEP_GRAPH=0: always launch eagerly)
   const char* ss = getenv("PPB_SINGLE_STREAM");
   n->single_stream = (ss && ss[0] == '1') ? 1 : 0;
   // created up front: a training step must be capturable in a CUDA graph right after its first eager run
