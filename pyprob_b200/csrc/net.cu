@@ -827,14 +827,14 @@ __global__ void __launch_bounds__(256) k_dgates_reduce(const float* __restrict__
                                                         const int* __restrict__ step_nrows, const int* __restrict__ row_prev,
                                                         const ppb_addr_desc* __restrict__ addrs, int H4, int S, int I, int E,
                                                         float* __restrict__ d_pstep, float* __restrict__ grad,
-                                                        int64_t w_ih_off) {
+                                                        int64_t w_ih_off, int slab) {
   __shared__ float s_emb[kRedSlab][8];
   __shared__ float s_dot[kRedSlab][8];
   __shared__ float acc_b[8];
   __shared__ float acc_w[8][heads::CMAX];
   const int st = blockIdx.y;
-  const int seg0 = step_row0[st], r0 = seg0 + blockIdx.x * kRedSlab;
-  int r1 = r0 + kRedSlab;
+  const int seg0 = step_row0[st], r0 = seg0 + blockIdx.x * slab;   // slab <= kRedSlab rows per block
+  int r1 = r0 + slab;
   if (r1 > seg0 + step_nrows[st]) r1 = seg0 + step_nrows[st];
   if (r0 >= r1) return;
   const int pa = step_prev[st];
