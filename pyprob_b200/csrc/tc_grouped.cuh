@@ -261,7 +261,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_grouped(const Problem* __restri
           for (int j = 0; j < 8; ++j) {
             const int r = rb + j;
             const int64_t pos_k = span0 + r * 32 + ((((lane >> 2) ^ (r & 7))) << 2) + (lane & 3);
-            mk[j] = (do_mask && r < rows) ? __ldg(mask_p + pos_k) : 1.0f;
+            // explicit loads into distinct registers, issued back to back (the compiler folded the predicated __ldg's into
+            // one register and serialised them)
+            mk[j] = 1.0f;
+            if (do_mask && r < rows) asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(mk[j]) : "l"(mask_p + pos_k));
           }
         }
 #pragma unroll

@@ -22,7 +22,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import _lib, parallel, util
+from . import _lib, ops, parallel, util
 from ._lib import call, ptr, stream
 from .encoding import EncodedBatch
 from .util import InferenceNetwork as InferenceNetworkType  # noqa: F401
@@ -935,7 +935,7 @@ class InferenceNetworkLSTM(nn.Module):
         def par(x):
             if x is None:
                 return None, 0, None
-            t = torch.as_tensor(x, dtype=torch.float32, device='cuda').reshape(-1).contiguous()
+            t = ops._f32(x, 'cuda').reshape(-1)      # python scalars: cached device constants (no host->device copy)
             return t, (0 if t.numel() == 1 else 1), t
         p0, s0, k0 = par(prior0)
         p1, s1, k1 = par(prior1)

@@ -9,8 +9,21 @@ from . import _lib
 from ._lib import call, ptr, stream
 
 
+_scalar_cache = {}
+
+
 def _f32(t, device):
     if not torch.is_tensor(t):
+        if isinstance(t, (int, float)):
+            # python scalars (distribution parameters shared by all particles): a host->device copy of a pageable scalar is a
+            # full stream synchronisation; keep one device constant per value instead (filled by a kernel, no copy)
+            key = (float(t), str(device))
+            c = _scalar_cache.get(key)
+            if c is None:
+                if len(_scalar_cache) > 4096:
+                    _scalar_cache.clear()
+                c = _scalar_cache[key] = torch.full((1,), float(t), dtype=torch.float32, device=device)
+            return c
         t = torch.tensor(t, dtype=torch.float32, device=device)
     return t.to(device=device, dtype=torch.float32).contiguous()
 

@@ -96,6 +96,8 @@ def _inflate(distribution):
 
 
 def _broadcast_value(value, n):
+    if isinstance(value, (int, float)):      # observed constants: filled on the device, no host->device copy (= no sync)
+        return torch.full((n,), float(value), dtype=torch.float32, device='cuda')
     v = torch.as_tensor(value, dtype=torch.float32).to('cuda').reshape(-1)
     if v.numel() == 1 and n > 1:
         v = v.expand(n).contiguous()
