@@ -192,8 +192,10 @@ def cpu_reference_arm(steps, warmup, budget_s=20.0):
             best = (nt, dt)
     threads = best[0]
     torch.set_num_threads(threads)
-    for _ in range(max(warmup, 1)):
+    tw, nw = time.perf_counter(), 0
+    while nw < max(warmup, 1) or time.perf_counter() - tw < 1.0:   # thread pool and allocator settle for about a second
         one_step()
+        nw += 1
     t0 = time.perf_counter()
     done = 0
     for _ in range(steps):

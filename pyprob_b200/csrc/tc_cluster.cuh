@@ -83,11 +83,23 @@ struct __align__(1024) Smem {
 };
 inline size_t smem_bytes() { return sizeof(Smem) + 1024; }
 
+// optional phase clock (ppb_debug_trace): CTA 0 stamps %globaltimer at the phase boundaries; slots as in tcg::k_grouped plus
+// 7 = partials of the whole cluster visible
+#define TCC_TRACE(slot)                                                                                   \
+  do {                                                                                                    \
+    if (trace && blockIdx.x == 0) {                                                                       \
+      unsigned long long _t;                                                                              \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                                              \
+      trace[slot] = _t;                                                                                   \
+    }                                                                                                     \
+  } while (0)
+
 // Mainloop over this CTA's K-slice [c0, c1) of output tile (mt, nt), then the partial tile parked in shared memory.
 // Called by all threads; returns after the first cluster barrier (every partial of the cluster is readable).
 template <bool X3>
 __device__ __forceinline__ void mainloop_and_park(Smem& sm, const tcg::Operand& A, const tcg::Operand& B, int mt, int nt,
-                                                  int c0, int c1, uint32_t tmem, int warp, int lane) {
+                                                  int c0, int c1, uint32_t tmem, int warp, int lane,
+                                                  unsigned long long* trace = nullptr) {
   if (warp == 0) {
     if (lane == 0) {
       const uint32_t bytes = (tcg::stage_bytes(A, mt) + tcg::stage_bytes(B, nt)) * (X3 ? 2u : 1u);
@@ -108,6 +120,7 @@ __device__ __forceinline__ void mainloop_and_park(Smem& sm, const tcg::Operand& 
         int s = (c - c0) % tcg::kStages;
         uint32_t ph = ((c - c0) / tcg::kStages) & 1;
         mbar_wait(&sm.full[s], ph);
+        if (c == c0) TCC_TRACE(2);
         fence_after_sync();
         uint32_t sa_hi = smem_u32(sm.a_hi[s]), sa_lo = smem_u32(sm.a_lo[s]);
         uint32_t sb_hi = smem_u32(sm.b_hi[s]), sb_lo = smem_u32(sm.b_lo[s]);
@@ -126,12 +139,14 @@ __device__ __forceinline__ void mainloop_and_park(Smem& sm, const tcg::Operand& 
         mma_commit(&sm.empty[s]);
       }
       mma_commit(&sm.tmem_full);
+      TCC_TRACE(3);
     }
   } else {
     // thread = TMEM lane = row of the tile; 32 consecutive columns per load
     const int q = warp & 3, cb = (warp - 2) >> 2;
     float* part = reinterpret_cast<float*>(sm.a_hi);
     mbar_wait(&sm.tmem_full, 0);
+    if (threadIdx.x == 64) TCC_TRACE(4);
     fence_after_sync();
     float v[32];
     if (c1 > c0) {
@@ -158,6 +173,7 @@ __device__ __forceinline__ void mainloop_and_park(Smem& sm, const tcg::Operand& 
   fence_before_sync();
   cluster_sync_all();
   fence_after_sync();
+  if (threadIdx.x == 64) TCC_TRACE(7);
 }
 
 // sum of the CS partials at (row, lane + 32 g), g = 0..3, in fixed split order
@@ -189,7 +205,9 @@ __device__ __forceinline__ void common_setup(Smem& sm, int warp, int lane) {
 // ---- generic flavours -------------------------------------------------------------------------------------------------
 // grid = (sum of tiles) * CS, cluster (CS, 1, 1): blockIdx.x / CS = tile, %cluster_ctarank = K-split.
 template <bool X3, int CS, int EPI>
-__global__ void __launch_bounds__(tcg::kThreads, 1) k_cluster(const tcg::Problem* __restrict__ probs, int n_probs) {
+__global__ void __launch_bounds__(tcg::kThreads, 1) k_cluster(const tcg::Problem* __restrict__ probs, int n_probs,
+                                                                 unsigned long long* __restrict__ trace) {
+  if (threadIdx.x == 0) TCC_TRACE(0);
   extern __shared__ uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -210,7 +228,8 @@ __global__ void __launch_bounds__(tcg::kThreads, 1) k_cluster(const tcg::Problem
   const int c0 = (int)((int64_t)KC * split / CS), c1 = (int)((int64_t)KC * (split + 1) / CS);
   common_setup(sm, warp, lane);
   const uint32_t tmem = sm.tmem_base;
-  mainloop_and_park<X3>(sm, P.a, P.b, mt, nt, c0, c1, tmem, warp, lane);
+  if (threadIdx.x == 0) TCC_TRACE(1);
+  mainloop_and_park<X3>(sm, P.a, P.b, mt, nt, c0, c1, tmem, warp, lane, trace);
 
   if (warp >= 2) {
     constexpr int kRowsPerCta = 128 / CS, kRowsPerWarp = kRowsPerCta / tcg::kEpiWarps;
@@ -259,18 +278,28 @@ __global__ void __launch_bounds__(tcg::kThreads, 1) k_cluster(const tcg::Problem
     }
   }
   // nobody leaves (and frees its shared memory) while a peer may still be reading its partial
+  if (threadIdx.x == 64) TCC_TRACE(5);
   fence_before_sync();
   cluster_sync_all();
+  if (threadIdx.x == 0) TCC_TRACE(6);
   if (warp == 1) {
     fence_after_sync();
     tmem_dealloc<tcg::kTmemCols>(tmem);
+  }
+  if (threadIdx.x == 0 && trace && blockIdx.x == 0) {
+    const int dm[3] = {P.M, P.N, P.K};
+    trace[13] = 1ull + CS * 16;
+    trace[8] = (unsigned long long)dm[0]; trace[9] = (unsigned long long)dm[1]; trace[10] = (unsigned long long)dm[2];
+    trace[11] = (unsigned long long)gridDim.x; trace[12] = (unsigned long long)(c1 - c0);
   }
 }
 
 // ---- LSTM time step: recurrent GEMM + cell in the reduce phase --------------------------------------------------------------
 // Step list and CellIO as in tc_lstm.cuh (gate-interleaved W_hh: tile column g * 32 + j = gate g of unit nt * 32 + j).
 template <bool X3, int CS>
-__global__ void __launch_bounds__(tcg::kThreads, 1) k_lstm_cluster(const tcl::Step* __restrict__ steps, int n_steps) {
+__global__ void __launch_bounds__(tcg::kThreads, 1) k_lstm_cluster(const tcl::Step* __restrict__ steps, int n_steps,
+                                                                      unsigned long long* __restrict__ trace) {
+  if (threadIdx.x == 0) TCC_TRACE(0);
   extern __shared__ uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -292,7 +321,8 @@ __global__ void __launch_bounds__(tcg::kThreads, 1) k_lstm_cluster(const tcl::St
   const int c0 = (int)((int64_t)KC * split / CS), c1 = (int)((int64_t)KC * (split + 1) / CS);
   common_setup(sm, warp, lane);
   const uint32_t tmem = sm.tmem_base;
-  mainloop_and_park<X3>(sm, P.a, P.b, mt, nt, c0, c1, tmem, warp, lane);
+  if (threadIdx.x == 0) TCC_TRACE(1);
+  mainloop_and_park<X3>(sm, P.a, P.b, mt, nt, c0, c1, tmem, warp, lane, trace);
 
   if (warp >= 2) {
     constexpr int kRowsPerCta = 128 / CS, kRowsPerWarp = kRowsPerCta / tcg::kEpiWarps;
@@ -359,11 +389,19 @@ __global__ void __launch_bounds__(tcg::kThreads, 1) k_lstm_cluster(const tcl::St
       tcg::st_global(io.hmn_lo + pos_mn, hl);
     }
   }
+  if (threadIdx.x == 64) TCC_TRACE(5);
   fence_before_sync();
   cluster_sync_all();
+  if (threadIdx.x == 0) TCC_TRACE(6);
   if (warp == 1) {
     fence_after_sync();
     tmem_dealloc<tcg::kTmemCols>(tmem);
+  }
+  if (threadIdx.x == 0 && trace && blockIdx.x == 0) {
+    const int dm[3] = {P.M, 4 * io.H, io.H};
+    trace[13] = 2ull + CS * 16;
+    trace[8] = (unsigned long long)dm[0]; trace[9] = (unsigned long long)dm[1]; trace[10] = (unsigned long long)dm[2];
+    trace[11] = (unsigned long long)gridDim.x; trace[12] = (unsigned long long)(c1 - c0);
   }
 }
 

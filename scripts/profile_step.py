@@ -50,15 +50,22 @@ for k, c, avg, t in sorted(rows, key=lambda r: -r[3])[:25]:
     print('%-72s n=%4d avg=%8.1f us total=%9.1f us %5.1f%%' % (k, c, avg, t, 100 * t / tot))
 print('device total per step: %.1f us' % (tot / 5))
 
-# per-launch phase stamps of the tensor-core grouped GEMM (CTA 0 of each launch of one step)
-tr = torch.zeros(64 * 16, dtype=torch.int64, device=dev)
+# per-launch phase stamps of the tensor-core GEMM kernels (CTA 0 of each launch of one step)
+NTR = 256
+tr = torch.zeros(NTR * 16, dtype=torch.int64, device=dev)
 call('ppb_debug_trace', ptr(tr))
 step()
 torch.cuda.synchronize()
 call('ppb_debug_trace', None)
-t = tr.cpu().numpy().reshape(64, 16)
-for i in range(64):
+t = tr.cpu().numpy().reshape(NTR, 16)
+kinds = {0: 'grouped'}
+prev_end = None
+for i in range(NTR):
     if t[i, 0] == 0: break
     r = t[i]
-    print('tc launch %2d: M%5d N%5d K%5d grid%4d chunks%3d | setup %5d first_data %5d mma_done %5d acc_ready %5d epi_done %5d end %5d ns' % (
-        i, r[8], r[9], r[10], r[11], r[12], r[1]-r[0], r[2]-r[0], r[3]-r[0], r[4]-r[0], r[5]-r[0], r[6]-r[0]))
+    kind = int(r[13]); name = 'grouped' if kind == 0 else ('cluster' if kind % 16 == 1 else 'lstm_cl') + 'x%d' % (kind // 16)
+    vis = (r[7] - r[0]) if r[7] else -1
+    print('tc launch %3d %-10s: M%5d N%5d K%5d grid%4d chunks%3d | setup %5d first_data %5d mma_issued %5d acc_ready %5d cluster_vis %5d epi_done %5d end %5d ns | start %+7d ns after previous end' % (
+        i, name, r[8], r[9], r[10], r[11], r[12], r[1]-r[0], r[2]-r[0], r[3]-r[0], r[4]-r[0], vis, r[5]-r[0], r[6]-r[0],
+        (r[0] - prev_end) if prev_end is not None else 0))
+    prev_end = r[6]
