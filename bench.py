@@ -647,17 +647,21 @@ def _gum_model():
 
 
 def _time_posterior(model, n, engine, reps):
+    """Wall-clock seconds of `reps` posterior_results calls, one at a time (each ends with a device->host read of the ESS).
+    Returns (particles/s over ALL reps, ess, per-call stats in ms): the headline is the plain total, the median / p90 / max
+    show whether a single call stalled (the calls are ~1 ms, a host hiccup of tens of ms is visible here)."""
     obs = {'obs0': 8, 'obs1': 9}
     for _ in range(2):
         model.posterior_results(n, engine, observe=obs)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
     ess = 0.0
+    ms = []
     for _ in range(reps):
+        t0 = time.perf_counter()
         post = model.posterior_results(n, engine, observe=obs)
         ess = float(post.effective_sample_size)   # device->host read of the result
-    torch.cuda.synchronize()
-    return reps * n / (time.perf_counter() - t0), ess
+        ms.append((time.perf_counter() - t0) * 1e3)
+    return reps * n / (sum(ms) * 1e-3), ess, percentile_stats(ms)
 
 
 def _cpu_entry(done, spent, what):
@@ -676,12 +680,12 @@ def posterior_is_workload(dev, budget_s=3.0):
     pyprob.seed(1)
     pyprob.set_verbosity(0)
     m = _gum_model()
-    value, ess = _time_posterior(m, 65536, InferenceEngine.IMPORTANCE_SAMPLING, 10)
-    big, _ = _time_posterior(m, 1 << 24, InferenceEngine.IMPORTANCE_SAMPLING, 3)
+    value, ess, stats = _time_posterior(m, 65536, InferenceEngine.IMPORTANCE_SAMPLING, 20)
+    big, _, _ = _time_posterior(m, 1 << 24, InferenceEngine.IMPORTANCE_SAMPLING, 3)
     done, spent = _timed_cpu(lambda n: opost.gum_is(n), 2000, budget_s)
     cb = _cpu_entry(done, spent, 'prior draw + two Normal log_probs + float sum per particle')
     return {'metric': 'is_posterior_particles_per_sec', 'value': value, 'unit': 'particles/s', 'particles': 65536,
-            'ess': ess, 'value_at_16M_particles': big, 'cpu_baseline': cb, 'ratio_to_cpu_baseline': value / cb['value'],
+            'ess': ess, 'ms_per_call': stats, 'value_at_16M_particles': big, 'cpu_baseline': cb, 'ratio_to_cpu_baseline': value / cb['value'],
             'config': 'GaussianUnknownMean, observe obs0=8 obs1=9, Model.posterior_results (BASELINE configs[0] at 64k)'}
 
 
@@ -698,7 +702,7 @@ def posterior_ic_gum_workload(dev, budget_s=4.0):
     with contextlib.redirect_stdout(io.StringIO()):
         m.learn_inference_network(num_traces=10 * 256, batch_size=256, inference_network=InferenceNetwork.LSTM,
                                   lstm_dim=512, observe_embeddings={'obs0': {'dim': 32}, 'obs1': {'dim': 32}})
-    value, ess = _time_posterior(m, 65536, InferenceEngine.IMPORTANCE_SAMPLING_WITH_INFERENCE_NETWORK, 5)
+    value, ess, stats = _time_posterior(m, 65536, InferenceEngine.IMPORTANCE_SAMPLING_WITH_INFERENCE_NETWORK, 20)
     net = m._inference_network
     P = {k: v.cpu() for k, v in net.reference_state_dict().items()}
     address = next(iter(net._addresses))
@@ -707,7 +711,7 @@ def posterior_ic_gum_workload(dev, budget_s=4.0):
     cb = _cpu_entry(done, spent, 'observe embedding once, then per particle one LSTM step (h=512) + mixture proposal '
                                  'draw + log p - log q + two observe scores')
     return {'metric': 'ic_posterior_particles_per_sec', 'value': value, 'unit': 'particles/s', 'particles': 65536,
-            'ess': ess, 'cpu_baseline': cb, 'ratio_to_cpu_baseline': value / cb['value'],
+            'ess': ess, 'ms_per_call': stats, 'cpu_baseline': cb, 'ratio_to_cpu_baseline': value / cb['value'],
             'config': 'GaussianUnknownMean, LSTM h=512 proposal network (same weights on both sides), 64k particles'}
 
 
@@ -743,7 +747,7 @@ def posterior_ic_marsaglia_workload(dev, budget_s=5.0):
         warnings.simplefilter('ignore')
         m.learn_inference_network(num_traces=20 * 1024, batch_size=1024, inference_network=InferenceNetwork.LSTM,
                                   lstm_dim=512, observe_embeddings={'obs0': {'dim': 32}, 'obs1': {'dim': 32}})
-        value, ess = _time_posterior(m, 65536, InferenceEngine.IMPORTANCE_SAMPLING_WITH_INFERENCE_NETWORK, 3)
+        value, ess, stats = _time_posterior(m, 65536, InferenceEngine.IMPORTANCE_SAMPLING_WITH_INFERENCE_NETWORK, 10)
     net = m._inference_network
     P = {k: v.cpu() for k, v in net.reference_state_dict().items()}
     table = {}
@@ -756,7 +760,7 @@ def posterior_ic_marsaglia_workload(dev, budget_s=5.0):
     cb = _cpu_entry(done, spent, 'rejection loop, per site one LSTM step (h=512) + truncated-normal-mixture proposal '
                                  'draw + log p - log q')
     return {'metric': 'ic_posterior_particles_per_sec', 'value': value, 'unit': 'particles/s', 'particles': 65536,
-            'ess': ess, 'addresses': len(net._addresses), 'cpu_baseline': cb, 'ratio_to_cpu_baseline': value / cb['value'],
+            'ess': ess, 'ms_per_call': stats, 'addresses': len(net._addresses), 'cpu_baseline': cb, 'ratio_to_cpu_baseline': value / cb['value'],
             'config': 'GaussianUnknownMeanMarsaglia, LSTM h=512 (same weights on both sides), 64k particles (BASELINE configs[2])'}
 
 

@@ -63,6 +63,8 @@ __device__ __forceinline__ void ppb_adam_update(float& p, float g, float& m, flo
 
 // ---- math constants (fp32, written the way torch.distributions writes them) -------------------
 #define PPB_LOG_SQRT_2PI 0.9189385332046727f  // math.log(math.sqrt(2*math.pi))
+#define PPB_LOG2E 1.4426950408889634f
+#define PPB_LN2 0.6931471805599453f
 #define PPB_INV_SQRT2 0.7071067811865476f
 #define PPB_EPS32 1.1920928955078125e-07f     // torch.finfo(torch.float32).eps
 #define PPB_LOG_EPSILON (-18.420680743952367f) // pyprob/util.py:35 log(1e-8)
@@ -72,6 +74,31 @@ __device__ __forceinline__ float ppb_normal_lp(float v, float mu, float sigma) {
   float var = sigma * sigma;
   float d = v - mu;
   return -(d * d) / (2.0f * var) - logf(sigma) - PPB_LOG_SQRT_2PI;
+}
+
+// LSTM cell activations, branch-free (the libm forms carry a slow-path branch each — division, tanhf's range split — which cut
+// the epilogue of the fused LSTM kernels into one basic block per gate and kept the loads of different rows from overlapping;
+// they were also a third of its instructions).  EX2 / RCP approximations: sigmoid within 3e-7 relative; tanh within 4e-7
+// relative (odd Taylor polynomial to x^9 below 0.25, 1 - 2 / (1 + exp(2|x|)) above).  Every cell kernel, fused or not,
+// forward or backward, goes through these two, so all variants agree to the last bit of the activation.
+__device__ __forceinline__ float ppb_cell_sigmoid(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -PPB_LOG2E));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+__device__ __forceinline__ float ppb_cell_tanh(float x) {
+  const float ax = fabsf(x);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * (2.0f * PPB_LOG2E)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  const float big = fmaf(-2.0f, r, 1.0f);
+  const float x2 = ax * ax;
+  float p = fmaf(x2, 62.0f / 2835.0f, -17.0f / 315.0f);
+  p = fmaf(x2, p, 2.0f / 15.0f);
+  p = fmaf(x2, p, -1.0f / 3.0f);
+  const float small = fmaf(ax * x2, p, ax);
+  return copysignf(ax < 0.25f ? small : big, x);
 }
 
 __device__ __forceinline__ float ppb_std_normal_cdf(float x) {

@@ -462,13 +462,13 @@ __global__ void __launch_bounds__(256) k_cell_fwd(float* __restrict__ gates, con
       }
       pre[g] = v;
     }
-    float ig = 1.0f / (1.0f + expf(-pre[0]));
-    float fg = 1.0f / (1.0f + expf(-pre[1]));
-    float gg = tanhf(pre[2]);
-    float og = 1.0f / (1.0f + expf(-pre[3]));
+    float ig = ppb_cell_sigmoid(pre[0]);
+    float fg = ppb_cell_sigmoid(pre[1]);
+    float gg = ppb_cell_tanh(pre[2]);
+    float og = ppb_cell_sigmoid(pre[3]);
     float cp = (t > 0) ? c[(int64_t)row_prev[row] * H + j] : 0.0f;
     float cn = fg * cp + ig * gg;
-    float hn = og * tanhf(cn);
+    float hn = og * ppb_cell_tanh(cn);
     gates[(int64_t)row * 4 * H + j] = ig;
     gates[(int64_t)row * 4 * H + H + j] = fg;
     gates[(int64_t)row * 4 * H + 2 * H + j] = gg;
@@ -658,42 +658,65 @@ __global__ void __launch_bounds__(256) k_cell_bwd(const float* __restrict__ gate
                                                    float* __restrict__ d_pobs, const int* __restrict__ row_prev,
                                                    const int* __restrict__ row_next, const int* __restrict__ row_trace,
                                                    HImg gimg, int row0, int n_rows, int H, int t) {
-  int64_t total = (int64_t)n_rows * H;
+  // Index arithmetic once per (row, unit): the four gate columns j, H + j, 2H + j, 3H + j sit H / 32 column blocks apart
+  // (H % 32 == 0 on this path), so their image positions differ by a constant; the kernel used to spend most of its
+  // instructions on four independent 64-bit offset computations per format.
+  const int64_t total = (int64_t)n_rows * H;
+  const int64_t gate_stride = (int64_t)(H >> 5) * tc::kTileFloats;
+  const bool h32 = (H & 31) == 0;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    int i = (int)(e / H), j = (int)(e % H);
-    int row = row0 + i;
-    int tr = row_trace[row];
-    float* dgr = dgates + (int64_t)row * 4 * H;
-    if (tr < 0) {
-      dgr[j] = 0.f; dgr[H + j] = 0.f; dgr[2 * H + j] = 0.f; dgr[3 * H + j] = 0.f;
-      if (gimg.k_hi)
-        for (int g4 = 0; g4 < 4; ++g4) tcg::img_store(gimg.k_hi, gimg.k_lo, gimg.mn_hi, gimg.mn_lo, row, g4 * H + j, gimg.kb, 0.0f);
-      continue;
+    const int i = (int)(e / H), j = (int)(e - (int64_t)i * H);
+    const int row = row0 + i;
+    const int tr = __ldg(row_trace + row);
+    const int64_t rH = (int64_t)row * H + j;       // position in [R, H] tensors
+    float* dgr = dgates + (int64_t)row * 4 * H + j;
+    float dv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (tr >= 0) {
+      const int nx = __ldg(row_next + row);
+      const float* g = gates + (int64_t)row * 4 * H + j;
+      const float ig = g[0], fg = g[H], gg = g[2 * H], og = g[3 * H];
+      const float cn = c[rH];
+      const float cp = (t > 0) ? c[(int64_t)__ldg(row_prev + row) * H + j] : 0.0f;
+      const float tc_ = ppb_cell_tanh(cn);
+      const bool has_next = nx >= 0;
+      const float dht = dh[rH] + (has_next ? dh_rec[rH] : 0.0f);
+      const float dct = (has_next ? dc[(int64_t)nx * H + j] : 0.0f) + dht * og * (1.0f - tc_ * tc_);
+      dv[0] = dct * gg * ig * (1.0f - ig);
+      dv[1] = dct * cp * fg * (1.0f - fg);
+      dv[2] = dct * ig * (1.0f - gg * gg);
+      dv[3] = dht * tc_ * og * (1.0f - og);
+      dc[rH] = dct * fg;
+      float* dp = d_pobs + (int64_t)tr * 4 * H + j;
+      if (has_next) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dp[q * H] += dv[q];
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dp[q * H] = dv[q];
+      }
     }
-    const int nx = row_next[row];
-    const float* g = gates + (int64_t)row * 4 * H;
-    float ig = g[j], fg = g[H + j], gg = g[2 * H + j], og = g[3 * H + j];
-    float cn = c[(int64_t)row * H + j];
-    float cp = (t > 0) ? c[(int64_t)row_prev[row] * H + j] : 0.0f;
-    float tc = tanhf(cn);
-    bool has_next = nx >= 0;
-    float dht = dh[(int64_t)row * H + j] + (has_next ? dh_rec[(int64_t)row * H + j] : 0.0f);
-    float dct = (has_next ? dc[(int64_t)nx * H + j] : 0.0f) + dht * og * (1.0f - tc * tc);
-    float di = dct * gg * ig * (1.0f - ig);
-    float df = dct * cp * fg * (1.0f - fg);
-    float dg = dct * ig * (1.0f - gg * gg);
-    float d_o = dht * tc * og * (1.0f - og);
-    dc[(int64_t)row * H + j] = dct * fg;
-    dgr[j] = di; dgr[H + j] = df; dgr[2 * H + j] = dg; dgr[3 * H + j] = d_o;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dgr[q * H] = dv[q];
     if (gimg.k_hi) {
-      tcg::img_store(gimg.k_hi, gimg.k_lo, gimg.mn_hi, gimg.mn_lo, row, j, gimg.kb, di);
-      tcg::img_store(gimg.k_hi, gimg.k_lo, gimg.mn_hi, gimg.mn_lo, row, H + j, gimg.kb, df);
-      tcg::img_store(gimg.k_hi, gimg.k_lo, gimg.mn_hi, gimg.mn_lo, row, 2 * H + j, gimg.kb, dg);
-      tcg::img_store(gimg.k_hi, gimg.k_lo, gimg.mn_hi, gimg.mn_lo, row, 3 * H + j, gimg.kb, d_o);
+      if (h32) {
+        const int64_t ok = tc::packed_offset(row, j, gimg.kb), omn = tc::packed_offset_mn(row, j, gimg.kb);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float hi, lo;
+          tc::split_tf32(dv[q], hi, lo);
+          gimg.k_hi[ok + q * gate_stride] = hi;
+          if (gimg.k_lo) gimg.k_lo[ok + q * gate_stride] = lo;
+          if (gimg.mn_hi) {
+            gimg.mn_hi[omn + q * gate_stride] = hi;
+            if (gimg.mn_lo) gimg.mn_lo[omn + q * gate_stride] = lo;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          tcg::img_store(gimg.k_hi, gimg.k_lo, gimg.mn_hi, gimg.mn_lo, row, q * H + j, gimg.kb, dv[q]);
+      }
     }
-    float* dp = d_pobs + (int64_t)tr * 4 * H;
-    if (has_next) { dp[j] += di; dp[H + j] += df; dp[2 * H + j] += dg; dp[3 * H + j] += d_o; }
-    else { dp[j] = di; dp[H + j] = df; dp[2 * H + j] = dg; dp[3 * H + j] = d_o; }
   }
 }
 
@@ -1506,14 +1529,14 @@ __global__ void __launch_bounds__(256) k_cell_infer(const float* __restrict__ re
       }
       pre[g] = v;
     }
-    float ig = 1.0f / (1.0f + expf(-pre[0]));
-    float fg = 1.0f / (1.0f + expf(-pre[1]));
-    float gg = tanhf(pre[2]);
-    float og = 1.0f / (1.0f + expf(-pre[3]));
+    float ig = ppb_cell_sigmoid(pre[0]);
+    float fg = ppb_cell_sigmoid(pre[1]);
+    float gg = ppb_cell_tanh(pre[2]);
+    float og = ppb_cell_sigmoid(pre[3]);
     float cp = first ? 0.0f : c[i * H + j];
     float cn = fg * cp + ig * gg;
     c[i * H + j] = cn;
-    h[i * H + j] = og * tanhf(cn);
+    h[i * H + j] = og * ppb_cell_tanh(cn);
   }
 }
 

@@ -21,6 +21,12 @@ __device__ __forceinline__ float4 ldg_stream4(const float* p) {
   return r;
 }
 
+__device__ __forceinline__ float ldg_stream(const float* p) {
+  float r;
+  asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+
 struct Param {
   const float* p;
   int stride;  // 0 = scalar broadcast, 1 = per particle
@@ -61,24 +67,29 @@ struct Sink {
 
 // ---- two-parameter families ---------------------------------------------------------------------
 struct NormalOp {
-  __device__ __forceinline__ float operator()(float v, float a, float b) const { return ppb_normal_lp(v, a, b); }
+  static constexpr bool kTable = false;
+  __device__ __forceinline__ float operator()(float v, float a, float b, const float*) const { return ppb_normal_lp(v, a, b); }
 };
 struct UniformOp {
   // torch/distributions/uniform.py log_prob: log(lb*ub) - log(high-low), lb = low<=v, ub = high>v
-  __device__ __forceinline__ float operator()(float v, float lo, float hi) const {
+  static constexpr bool kTable = false;
+  __device__ __forceinline__ float operator()(float v, float lo, float hi, const float*) const {
     float inside = (lo <= v && hi > v) ? 0.0f : -INFINITY;
     return inside - logf(hi - lo);
   }
 };
 // log(k!) for the counts that actually occur (k < 64), correctly rounded from the double-precision lgamma: lgammaf costs
 // ~40 instructions per particle and made the Poisson kernel ALU-bound at 39 % of HBM; other values take lgammaf.
+// The table is copied to shared memory by every CTA: the lanes of a warp hold different counts, and a constant-bank read
+// with divergent indices is replayed once per distinct address (63 % of HBM), shared memory serves them in one pass.
 __constant__ float c_log_factorial[64];
 struct PoissonOp {
+  static constexpr bool kTable = true;
   // torch/distributions/poisson.py log_prob: xlogy(v, rate) - rate - lgamma(v+1)
-  __device__ __forceinline__ float operator()(float v, float rate, float) const {
+  __device__ __forceinline__ float operator()(float v, float rate, float, const float* tab) const {
     float xl = (v == 0.0f) ? 0.0f : v * logf(rate);
     const int k = (int)v;
-    const float lg = (v >= 0.0f && v < 64.0f && (float)k == v) ? c_log_factorial[k] : lgammaf(v + 1.0f);
+    const float lg = (v >= 0.0f && v < 64.0f && (float)k == v) ? tab[k] : lgammaf(v + 1.0f);
     return xl - rate - lg;
   }
 };
@@ -86,6 +97,11 @@ struct PoissonOp {
 template <class Op, bool VEC>
 __global__ void __launch_bounds__(kThreads) k_score2(const float* __restrict__ value, Param a, Param b, Sink out,
                                                       int64_t n, Op op) {
+  __shared__ float tab[Op::kTable ? 64 : 1];
+  if (Op::kTable) {
+    if (threadIdx.x < 64) tab[threadIdx.x] = c_log_factorial[threadIdx.x];
+    __syncthreads();
+  }
   int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t nth = (int64_t)gridDim.x * blockDim.x;
   if (VEC) {
@@ -98,12 +114,12 @@ __global__ void __launch_bounds__(kThreads) k_score2(const float* __restrict__ v
       a.load4(i, pa);
       b.load4(i, pb);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) r[j] = op(v[j], pa[j], pb[j]);
+      for (int j = 0; j < 4; ++j) r[j] = op(v[j], pa[j], pb[j], tab);
       out.put4(i, r);
     }
-    for (int64_t i = (n4 << 2) + tid; i < n; i += nth) out.put(i, op(__ldg(value + i), a.at(i), b.at(i)));
+    for (int64_t i = (n4 << 2) + tid; i < n; i += nth) out.put(i, op(__ldg(value + i), a.at(i), b.at(i), tab));
   } else {
-    for (int64_t i = tid; i < n; i += nth) out.put(i, op(__ldg(value + i), a.at(i), b.at(i)));
+    for (int64_t i = tid; i < n; i += nth) out.put(i, op(__ldg(value + i), a.at(i), b.at(i), tab));
   }
 }
 
@@ -159,9 +175,18 @@ __global__ void __launch_bounds__(kThreads) k_categorical(const float* __restric
 // (truncated components: sigma_k -> sigma_k Z_k, and -inf outside [low, high]): one exp and one reciprocal per component and
 // ONE log per particle instead of two logs, an exp and two divisions per component — these kernels are bound by the
 // transcendental/ALU rate, not by HBM (ncu: profiles/).  Same value as the reference's formula up to fp32 rounding.
-template <int KMAX, bool TRUNC>
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// EXACT: K == KMAX is known at compile time (the component loops carry no k < K predicates)
+template <int KMAX, bool TRUNC, bool EXACT = false>
 __device__ __forceinline__ float mixture_row(float v, const float* __restrict__ m, const float* __restrict__ s,
-                                             const float* __restrict__ p, int K, float lo, float hi) {
+                                             const float* __restrict__ p, int K_rt, float lo, float hi) {
+  const int K = EXACT ? KMAX : K_rt;
+  // Reciprocals, the exponentials and the final log use the hardware approximations (MUFU.RCP / EX2 / LG2: <= 2 ulp on the
+  // terms that matter — exp arguments are <= 0 and the largest term is exp(0) = 1 exactly): with IEEE divisions and expf the
+  // kernel issued 660 instructions per particle at K = 10 and was issue-bound at 0.72 of HBM (profiles/r02c_ncu_scoring.md).
   float pk[KMAX], a[KMAX], scale[KMAX];
   float psum = 0.0f;
 #pragma unroll
@@ -169,37 +194,40 @@ __device__ __forceinline__ float mixture_row(float v, const float* __restrict__ 
     pk[k] = (k < K) ? p[k] : 0.0f;
     psum += pk[k];
   }
-  const float inv_psum = 1.0f / psum;
+  const float inv_psum = fast_rcp(psum);
   float mx = -INFINITY;
-  bool any_nan = false;
+  bool bad = false;
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
     if (k < K) {
       const float mu = m[k], sg = s[k];
-      const float inv_sg = 1.0f / sg;
+      const float inv_sg = fast_rcp(sg);
       const float z = (v - mu) * inv_sg;
-      float norm = sg;                       // sigma (times the truncated mass)
+      float inv_norm = inv_sg;               // 1 / (sigma * truncated mass)
+      bool neg = !(sg >= 0.0f);
       if (TRUNC) {
         const float alpha = (lo - mu) * inv_sg, beta = (hi - mu) * inv_sg;
-        norm = sg * (ppb_std_normal_cdf(beta) - ppb_std_normal_cdf(alpha));
+        const float mass = ppb_std_normal_cdf(beta) - ppb_std_normal_cdf(alpha);
+        inv_norm = inv_sg * fast_rcp(mass);
+        neg = neg || !(mass >= 0.0f);
       }
-      a[k] = -0.5f * z * z;
-      scale[k] = ppb_clamp_prob(pk[k] * inv_psum) / norm;
-      any_nan = any_nan || (a[k] != a[k]) || (scale[k] != scale[k]) || !(norm >= 0.0f);
+      a[k] = (-0.5f * PPB_LOG2E) * z * z;   // exponent in base 2
+      scale[k] = ppb_clamp_prob(pk[k] * inv_psum) * inv_norm;
+      bad = bad || neg || (a[k] != a[k]) || (scale[k] != scale[k]);
       mx = fmaxf(mx, a[k]);
     }
   }
-  if (any_nan) return NAN;                   // log of a negative / NaN parameter poisons the row like the reference
+  if (bad) return NAN;                       // log of a negative / NaN parameter poisons the row like the reference
   if (TRUNC && !(v >= lo && v <= hi)) return -INFINITY;   // log(lb * ub) = -inf in every component
   if (mx == -INFINITY) return -INFINITY;     // torch.logsumexp of all -inf
   float acc = 0.0f;
 #pragma unroll
   for (int k = 0; k < KMAX; ++k)
-    if (k < K) acc += scale[k] * expf(a[k] - mx);
-  return mx + logf(acc) - PPB_LOG_SQRT_2PI;
+    if (k < K) acc = fmaf(scale[k], fast_ex2(a[k] - mx), acc);
+  return (mx + fast_lg2(acc)) * PPB_LN2 - PPB_LOG_SQRT_2PI;
 }
 
-template <int KMAX, bool TRUNC>
+template <int KMAX, bool TRUNC, bool EXACT = false>
 __global__ void __launch_bounds__(kThreads) k_mixture(const float* __restrict__ value,
                                                        const float* __restrict__ means,
                                                        const float* __restrict__ stddevs,
@@ -210,16 +238,18 @@ __global__ void __launch_bounds__(kThreads) k_mixture(const float* __restrict__ 
   for (int64_t i = tid; i < n; i += nth) {
     float lo = 0.f, hi = 0.f;
     if (TRUNC) { lo = low.at(i); hi = high.at(i); }
-    out.put(i, mixture_row<KMAX, TRUNC>(__ldg(value + i), means + i * row_stride, stddevs + i * row_stride,
-                                        probs + i * row_stride, K, lo, hi));
+    out.put(i, mixture_row<KMAX, TRUNC, EXACT>(__ldg(value + i), means + i * row_stride, stddevs + i * row_stride,
+                                               probs + i * row_stride, K, lo, hi));
   }
 }
 
-// Same arithmetic, parameters staged through shared memory: a CTA copies the contiguous [256, K] parameter rows
-// of its tile with coalesced 128-bit loads, then every thread reads its own row from shared memory (instead of 3K
-// strided 4-byte global loads per thread).  Requires densely packed rows (row_stride == K) and 16-byte aligned
-// arrays.  STATUS: opt-in (PPB_MIXTURE_STAGED=1) until its first hardware run — written after the round-1 GPU budget
-// was spent; results must equal k_mixture's to rounding.
+// Same arithmetic, parameters staged through shared memory.  A thread of k_mixture reads its own [K] rows with 3K strided
+// 4-byte loads: one warp-level load touches K different 128-byte lines, i.e. 3K * K load wavefronts per 32 particles (300 at
+// K = 10) — the load/store unit, not HBM, bounds that kernel.  Here a WARP owns 32 consecutive particles: it copies their
+// contiguous 32 x K parameter block with fully coalesced 4-byte loads (one wavefront each) into shared memory at an odd row
+// pitch, then every lane reads its own row conflict-free.  Only __syncwarp, no CTA barrier.  Requires densely packed rows
+// (row_stride == K).  Opt-in (PPB_MIXTURE_STAGED=1): results must equal k_mixture's to rounding
+// (tests/test_scoring_staged_gpu.py).
 template <int KMAX, bool TRUNC>
 __global__ void __launch_bounds__(kThreads) k_mixture_staged(const float* __restrict__ value,
                                                               const float* __restrict__ means,
@@ -227,40 +257,47 @@ __global__ void __launch_bounds__(kThreads) k_mixture_staged(const float* __rest
                                                               const float* __restrict__ probs, int K, Param low,
                                                               Param high, Sink out, int64_t n) {
   extern __shared__ __align__(16) float sm[];
-  float* sm_m = sm;
-  float* sm_s = sm + kThreads * K;
-  float* sm_p = sm + 2 * kThreads * K;
-  for (int64_t tile0 = (int64_t)blockIdx.x * kThreads; tile0 < n; tile0 += (int64_t)gridDim.x * kThreads) {
-    const int rows = (int)((n - tile0 < kThreads) ? (n - tile0) : kThreads);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pitch = K | 1;
+  float* wm = sm + (size_t)warp * 3 * 32 * pitch;
+  float* ws = wm + 32 * pitch;
+  float* wp = ws + 32 * pitch;
+  const int dr = 32 / K, dk = 32 % K;       // (row, component) of flat element idx + 32
+  const int64_t stride = (int64_t)gridDim.x * (kThreads / 32) * 32;
+  for (int64_t w0 = ((int64_t)blockIdx.x * (kThreads / 32) + warp) * 32; w0 < n; w0 += stride) {
+    const int rows = (int)((n - w0 < 32) ? (n - w0) : 32);
     const int cnt = rows * K;
-    const float* gm = means + tile0 * K;
-    const float* gs = stddevs + tile0 * K;
-    const float* gp = probs + tile0 * K;
-    for (int idx = threadIdx.x * 4; idx < cnt; idx += kThreads * 4) {
-      if (idx + 4 <= cnt) {
-        *reinterpret_cast<float4*>(sm_m + idx) = ldg_stream4(gm + idx);
-        *reinterpret_cast<float4*>(sm_s + idx) = ldg_stream4(gs + idx);
-        *reinterpret_cast<float4*>(sm_p + idx) = ldg_stream4(gp + idx);
-      } else {
-        for (int j = idx; j < cnt; ++j) {
-          sm_m[j] = __ldg(gm + j);
-          sm_s[j] = __ldg(gs + j);
-          sm_p[j] = __ldg(gp + j);
-        }
+    const float* gm = means + w0 * K;
+    const float* gs = stddevs + w0 * K;
+    const float* gp = probs + w0 * K;
+    // one array at a time: its K loads are issued together (independent requests in flight), then scattered into shared memory
+    const int r0 = lane / K, k0 = lane % K;
+    auto stage = [&](const float* __restrict__ g, float* __restrict__ w) {
+      float v[KMAX];
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        const int idx = lane + 32 * j;
+        v[j] = (j < K && idx < cnt) ? ldg_stream(g + idx) : 0.0f;
       }
-    }
-    __syncthreads();
-    if ((int)threadIdx.x < rows) {
-      const int64_t i = tile0 + threadIdx.x;
-      const float* m = sm_m + threadIdx.x * K;
-      const float* sd = sm_s + threadIdx.x * K;
-      const float* p = sm_p + threadIdx.x * K;
+      int r = r0, k = k0;
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        if (j < K && lane + 32 * j < cnt) w[r * pitch + k] = v[j];
+        r += dr; k += dk;
+        if (k >= K) { k -= K; ++r; }
+      }
+    };
+    stage(gm, wm);
+    stage(gs, ws);
+    stage(gp, wp);
+    __syncwarp();
+    if (lane < rows) {
+      const int64_t i = w0 + lane;
       float lo = 0.f, hi = 0.f;
       if (TRUNC) { lo = low.at(i); hi = high.at(i); }
-      const float r = mixture_row<KMAX, TRUNC>(__ldg(value + i), m, sd, p, K, lo, hi);
-      out.put(i, r);
+      out.put(i, mixture_row<KMAX, TRUNC>(__ldg(value + i), wm + lane * pitch, ws + lane * pitch, wp + lane * pitch, K, lo, hi));
     }
-    __syncthreads();
+    __syncwarp();
   }
 }
 
@@ -278,9 +315,8 @@ int launch_mixture(const float* value, const float* means, const float* stddevs,
   if (n == 0) return PPB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   int grid = ppb_grid_for(n, kThreads, 1);
-  if (mixture_staged_enabled() && row_stride == K && K <= 10 && aligned16(means) && aligned16(stddevs) &&
-      aligned16(probs)) {
-    size_t smem = (size_t)3 * kThreads * K * sizeof(float);
+  if (mixture_staged_enabled() && row_stride == K && K <= 10) {
+    size_t smem = (size_t)3 * kThreads * (K | 1) * sizeof(float);
     if (K <= 4)
       k_mixture_staged<4, TRUNC><<<grid, kThreads, smem, st>>>(value, means, stddevs, probs, K, low, high, out, n);
     else
@@ -290,6 +326,8 @@ int launch_mixture(const float* value, const float* means, const float* stddevs,
   }
   if (K <= 4)
     k_mixture<4, TRUNC><<<grid, kThreads, 0, st>>>(value, means, stddevs, probs, row_stride, K, low, high, out, n);
+  else if (K == 10)   // the proposal heads' component count (pyprob/nn/proposal_normal_mixture.py: mixture_components = 10)
+    k_mixture<10, TRUNC, true><<<grid, kThreads, 0, st>>>(value, means, stddevs, probs, row_stride, K, low, high, out, n);
   else if (K <= 10)
     k_mixture<10, TRUNC><<<grid, kThreads, 0, st>>>(value, means, stddevs, probs, row_stride, K, low, high, out, n);
   else if (K <= 32)

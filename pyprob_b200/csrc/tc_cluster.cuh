@@ -24,8 +24,13 @@ namespace tcc {
 
 using namespace tc;
 
-constexpr int kPitch = 129;                  // floats per row of the parked partial tile: bank = (row + col) mod 32
-constexpr int kPartFloats = 128 * kPitch;    // 66 KB, aliases the operand stages
+// Parked partial tile: 128 rows x 128 floats, row r at byte 512 r, the eight 16-byte chunks of every 128-byte segment permuted
+// by (chunk ^ (r & 7)).  The park phase (thread = row) writes 16-byte vectors — four lanes share a bank group, the minimum for a
+// 512-byte warp store — and a reduce-phase warp reads one whole, 128-byte ALIGNED segment of one row per request: with the
+// former odd pitch (129 floats) every remote read straddled two segments and distributed shared memory delivered 8-9 B/clk
+// per SM instead of the ~17 it is good for (profiles/r02d_phase_stamps_gum.txt).
+constexpr int kPitch = 128;
+constexpr int kPartFloats = 128 * kPitch;    // 64 KB, aliases the operand stages
 static_assert(kPartFloats * 4 <= 2 * tcg::kStages * kTileBytes, "partial tile must fit in the A stages");
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -44,7 +49,9 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t local_smem_addr, uint32
 }
 __device__ __forceinline__ float ld_cluster(uint32_t cluster_addr) {
   float v;
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+  // volatile keeps it behind the cluster barrier (volatile + memory clobber); no clobber of its own, so that independent global
+  // loads may be scheduled around it — nothing writes the parked tiles between the two cluster barriers
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr));
   return v;
 }
 
@@ -166,9 +173,13 @@ __device__ __forceinline__ void mainloop_and_park(Smem& sm, const tcg::Operand& 
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = 0.0f;
     }
-    const uint32_t dst = smem_u32(part + (q * 32 + lane) * kPitch + cb * 32);
+    const int prow = q * 32 + lane;
+    const uint32_t dst = smem_u32(part + prow * kPitch + cb * 32);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + 4 * j), "f"(v[j]) : "memory");
+    for (int j4 = 0; j4 < 8; ++j4)
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16 * (j4 ^ (prow & 7))), "f"(v[4 * j4]),
+                   "f"(v[4 * j4 + 1]), "f"(v[4 * j4 + 2]), "f"(v[4 * j4 + 3])
+                   : "memory");
   }
   fence_before_sync();
   cluster_sync_all();
@@ -179,7 +190,8 @@ __device__ __forceinline__ void mainloop_and_park(Smem& sm, const tcg::Operand& 
 // sum of the CS partials at (row, lane + 32 g), g = 0..3, in fixed split order
 template <int CS>
 __device__ __forceinline__ void reduce_row(const Smem& sm, int row, int lane, float (&v)[4]) {
-  const uint32_t local = smem_u32(reinterpret_cast<const float*>(sm.a_hi) + row * kPitch + lane);
+  const uint32_t local = smem_u32(reinterpret_cast<const float*>(sm.a_hi) + row * kPitch + ((((lane >> 2) ^ (row & 7))) << 2) +
+                                  (lane & 3));
 #pragma unroll
   for (int g = 0; g < 4; ++g) v[g] = 0.0f;
 #pragma unroll
@@ -242,42 +254,68 @@ __global__ void __launch_bounds__(tcg::kThreads, 1) k_cluster(const tcg::Problem
       const int n = nt * 128 + g * 32 + lane;
       bias[g] = (P.bias && n < P.N) ? __ldg(P.bias + n) : 0.0f;
     }
+    // descriptor fields in registers: the explicit stores below are compiler barriers, every P.x after one is a reload
+    const int pM = P.M, pN = P.N;
+    const int64_t ldc = P.ldc, o_kb = P.o_kb, orow0 = P.o_row0, ocb0 = P.o_col0 / 32 + nt * 4;
+    float* const c_p = P.c;
+    float* const ok_hi = P.o_k_hi; float* const ok_lo = P.o_k_lo;
+    float* const omn_hi = P.o_mn_hi; float* const omn_lo = P.o_mn_lo;
+    const float* const mask_p = P.mask_hi;
+    const int n_blocks = (pN - nt * 128 + 31) >> 5;     // 32-column blocks of this tile inside the (padded) width
+    // pass 1 (no stores): partial sums from the peers' shared memory and the ReLU-mask words of all rows in flight together
+    float r_x[kRowsPerWarp][4];
 #pragma unroll
     for (int rr = 0; rr < kRowsPerWarp; ++rr) {
       const int row = split * kRowsPerCta + ew * kRowsPerWarp + rr;   // row of the tile
       const int m = mt * 128 + row;
-      if (m >= P.M) continue;   // warp-uniform
+      const bool live = m < pM;   // no per-row branch: the rows of a warp form one basic block, their loads overlap
       float v[4];
       reduce_row<CS>(sm, row, lane, v);
-      const int64_t orow = (int64_t)P.o_row0 + m;
+      const int64_t orow = orow0 + m;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int n = nt * 128 + g * 32 + lane;
-        if (g * 32 >= ((P.N - nt * 128 + 31) & ~31)) continue;   // warp-uniform: column block beyond the (padded) width
         float x = v[g] + bias[g];
         x = do_relu ? fmaxf(x, 0.0f) : x;
-        x = (n < P.N && m < m_valid) ? x : 0.0f;
-        if (EPI == 0) {
-          if (P.c && n < P.N) tcg::st_global(P.c + (int64_t)m * P.ldc + n, x);
-        } else {
-          const int64_t ocb = P.o_col0 / 32 + nt * 4 + g;
-          const int64_t span = ((orow >> 7) * P.o_kb + ocb) * kTileFloats + (orow & 127) * 32;
+        x = (n < pN && m < m_valid) ? x : 0.0f;
+        if (EPI == 2) {
+          const int64_t span = ((orow >> 7) * o_kb + (ocb0 + g)) * kTileFloats + (orow & 127) * 32;
           const int64_t pos_k = span + ((((lane >> 2) ^ (int)(orow & 7))) << 2) + (lane & 3);
-          if (do_mask) x = (tcg::ld_global(P.mask_hi + pos_k) > 0.0f) ? x : 0.0f;
-          if (P.c && n < P.N) tcg::st_global(P.c + (int64_t)m * P.ldc + n, x);
+          const float mk = (do_mask && live && g < n_blocks) ? __ldg(mask_p + pos_k) : 1.0f;
+          x = (mk > 0.0f) ? x : 0.0f;
+        }
+        r_x[rr][g] = x;
+      }
+    }
+    if (threadIdx.x == 64) TCC_TRACE(14);
+    // pass 2: stores
+#pragma unroll
+    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+      const int row = split * kRowsPerCta + ew * kRowsPerWarp + rr;
+      const int m = mt * 128 + row;
+      if (m >= pM) continue;   // warp-uniform
+      const int64_t orow = orow0 + m;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int n = nt * 128 + g * 32 + lane;
+        if (g >= n_blocks) continue;   // warp-uniform: column block beyond the (padded) width
+        const float x = r_x[rr][g];
+        if (c_p && n < pN) tcg::st_global(c_p + (int64_t)m * ldc + n, x);
+        if (EPI == 2) {
+          const int64_t span = ((orow >> 7) * o_kb + (ocb0 + g)) * kTileFloats + (orow & 127) * 32;
+          const int64_t pos_k = span + ((((lane >> 2) ^ (int)(orow & 7))) << 2) + (lane & 3);
           float h, l;
           split_tf32(x, h, l);
-          if (P.o_k_hi) { tcg::st_global(P.o_k_hi + pos_k, h); tcg::st_global(P.o_k_lo + pos_k, l); }
-          if (P.o_mn_hi) {
+          if (ok_hi) { tcg::st_global(ok_hi + pos_k, h); tcg::st_global(ok_lo + pos_k, l); }
+          if (omn_hi) {
             const int64_t pos_mn = span + ((((lane >> 3) ^ (int)(orow & 3))) << 3) + (lane & 7);
-            tcg::st_global(P.o_mn_hi + pos_mn, h);
-            tcg::st_global(P.o_mn_lo + pos_mn, l);
+            tcg::st_global(omn_hi + pos_mn, h);
+            tcg::st_global(omn_lo + pos_mn, l);
           }
         }
       }
     }
   }
-  // nobody leaves (and frees its shared memory) while a peer may still be reading its partial
   if (threadIdx.x == 64) TCC_TRACE(5);
   fence_before_sync();
   cluster_sync_all();
@@ -296,7 +334,8 @@ __global__ void __launch_bounds__(tcg::kThreads, 1) k_cluster(const tcg::Problem
 
 // ---- LSTM time step: recurrent GEMM + cell in the reduce phase --------------------------------------------------------------
 // Step list and CellIO as in tc_lstm.cuh (gate-interleaved W_hh: tile column g * 32 + j = gate g of unit nt * 32 + j).
-template <bool X3, int CS>
+// SMAX: compile-time bound of the sample-embedding width S (4 = pyprob's default sample_embedding_dim, 8 = the general case)
+template <bool X3, int CS, int SMAX>
 __global__ void __launch_bounds__(tcg::kThreads, 1) k_lstm_cluster(const tcl::Step* __restrict__ steps, int n_steps,
                                                                       unsigned long long* __restrict__ trace) {
   if (threadIdx.x == 0) TCC_TRACE(0);
@@ -329,11 +368,11 @@ __global__ void __launch_bounds__(tcg::kThreads, 1) k_lstm_cluster(const tcl::St
     const int ew = warp - 2;
     const int H = io.H, H4 = 4 * io.H, S = io.S;
     const int u = nt * 32 + lane;     // hidden unit of this lane
-    float wsmp[4][8];
+    float wsmp[4][SMAX];
 #pragma unroll
     for (int g = 0; g < 4; ++g)
 #pragma unroll
-      for (int s = 0; s < 8; ++s) wsmp[g][s] = (s < S) ? __ldg(io.w_smp_t + (int64_t)s * H4 + g * H + u) : 0.0f;
+      for (int s = 0; s < SMAX; ++s) wsmp[g][s] = (s < S) ? __ldg(io.w_smp_t + (int64_t)s * H4 + g * H + u) : 0.0f;
     const int64_t hkb = io.hkb;
     // row metadata of all this warp's rows first: it heads every row's dependency chain
     int m_tr[kRowsPerWarp], m_st[kRowsPerWarp];
@@ -345,48 +384,72 @@ __global__ void __launch_bounds__(tcg::kThreads, 1) k_lstm_cluster(const tcl::St
       m_st[rr] = __ldg(io.row_step + row);
       m_rp[rr] = __ldg(io.row_prev + row);
     }
+    // Two passes over the warp's rows.  Pass 1 holds no stores (and no compiler barrier), so the loads of all rows — partial
+    // sums from the peers' shared memory, P_obs / P_step / c_{t-1} from L2 — are in flight together instead of one row's
+    // latency chain after the other; pass 2 writes the results.
+    // Pass 1 is ONE basic block (padding rows read row 0 of the segment and are zeroed afterwards — no per-row branch), with
+    // the pointers of the descriptor in registers (P lives in shared memory behind a generic pointer: every io.x is a load).
+    float r_act[kRowsPerWarp][4], r_c[kRowsPerWarp], r_h[kRowsPerWarp];
+    {
+      const float* const g_pobs = io.p_obs; const float* const g_pstep = io.p_step;
+      const float* const g_c = io.c; const float* const g_smp = io.smp_emb;
+      const int64_t seg_row0 = (int64_t)P.row0;
 #pragma unroll
-    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
-      const int trow = split * kRowsPerCta + ew * kRowsPerWarp + rr;
-      const int64_t row = (int64_t)P.row0 + mt * 128 + trow;     // global row of the step
-      const int tr = m_tr[rr];
-      float act[4] = {0.f, 0.f, 0.f, 0.f}, cn = 0.0f, hn = 0.0f;
-      if (tr >= 0) {   // warp-uniform
+      for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+        const int trow = split * kRowsPerCta + ew * kRowsPerWarp + rr;
+        const bool live = m_tr[rr] >= 0;
+        const int64_t row = live ? seg_row0 + mt * 128 + trow : seg_row0;     // global row of the step (a valid one)
+        const int tr = live ? m_tr[rr] : 0, st = live ? m_st[rr] : 0;
+        const int64_t rp = (live && m_rp[rr] >= 0) ? m_rp[rr] : 0;
         float v[4];
         reduce_row<CS>(sm, trow, lane, v);
-        const int st = m_st[rr];
-        const int64_t rp = m_rp[rr] < 0 ? 0 : m_rp[rr];
-        float sm_e[8];
+        float sm_e[SMAX];
 #pragma unroll
-        for (int s = 0; s < 8; ++s) sm_e[s] = (s < S) ? __ldg(io.smp_emb + row * S + s) : 0.0f;
-        const float cp = __ldcg(io.c + rp * H + u);
+        for (int s = 0; s < SMAX; ++s) sm_e[s] = (s < S) ? __ldg(g_smp + row * S + s) : 0.0f;
+        const float cp = __ldcg(g_c + rp * H + u);
+        float act[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int col = g * H + u;
           // same order of additions as k_cell_fwd: (P_obs + P_step) + recurrent, then the sample-embedding FMAs
-          float x = __ldg(io.p_obs + (int64_t)tr * H4 + col) + __ldg(io.p_step + (int64_t)st * H4 + col);
+          float x = __ldg(g_pobs + (int64_t)tr * H4 + col) + __ldg(g_pstep + (int64_t)st * H4 + col);
           x += v[g];
 #pragma unroll
-          for (int s = 0; s < 8; ++s)
+          for (int s = 0; s < SMAX; ++s)
             if (s < S) x = fmaf(sm_e[s], wsmp[g][s], x);
-          act[g] = (g == 2) ? tanhf(x) : 1.0f / (1.0f + expf(-x));
+          act[g] = (g == 2) ? ppb_cell_tanh(x) : ppb_cell_sigmoid(x);
         }
-        cn = act[1] * cp + act[0] * act[2];
-        hn = act[3] * tanhf(cn);
-      }
+        const float cn = act[1] * cp + act[0] * act[2];
+        const float hn = act[3] * ppb_cell_tanh(cn);
 #pragma unroll
-      for (int g = 0; g < 4; ++g) tcg::st_global(io.gates + row * H4 + g * H + u, act[g]);
-      tcg::st_global(io.c + row * H + u, cn);
-      tcg::st_global(io.h + row * H + u, hn);
-      const int64_t span = ((row >> 7) * hkb + nt) * kTileFloats + (row & 127) * 32;
-      float hh, hl;
-      split_tf32(hn, hh, hl);
-      const int64_t pos_k = span + ((((lane >> 2) ^ (int)(row & 7))) << 2) + (lane & 3);
-      tcg::st_global(io.hk_hi + pos_k, hh);
-      tcg::st_global(io.hk_lo + pos_k, hl);
-      const int64_t pos_mn = span + ((((lane >> 3) ^ (int)(row & 3))) << 3) + (lane & 7);
-      tcg::st_global(io.hmn_hi + pos_mn, hh);
-      tcg::st_global(io.hmn_lo + pos_mn, hl);
+        for (int g = 0; g < 4; ++g) r_act[rr][g] = live ? act[g] : 0.0f;
+        r_c[rr] = live ? cn : 0.0f;
+        r_h[rr] = live ? hn : 0.0f;
+      }
+    }
+    if (threadIdx.x == 64) TCC_TRACE(14);
+    {
+      float* const g_gates = io.gates; float* const g_c = io.c; float* const g_h = io.h;
+      float* const g_hk_hi = io.hk_hi; float* const g_hk_lo = io.hk_lo;
+      float* const g_hmn_hi = io.hmn_hi; float* const g_hmn_lo = io.hmn_lo;
+      const int64_t row_first = (int64_t)P.row0 + mt * 128 + split * kRowsPerCta + ew * kRowsPerWarp;
+#pragma unroll
+      for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+        const int64_t row = row_first + rr;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) tcg::st_global(g_gates + row * H4 + g * H + u, r_act[rr][g]);
+        tcg::st_global(g_c + row * H + u, r_c[rr]);
+        tcg::st_global(g_h + row * H + u, r_h[rr]);
+        const int64_t span = ((row >> 7) * hkb + nt) * kTileFloats + (row & 127) * 32;
+        float hh, hl;
+        split_tf32(r_h[rr], hh, hl);
+        const int64_t pos_k = span + ((((lane >> 2) ^ (int)(row & 7))) << 2) + (lane & 3);
+        tcg::st_global(g_hk_hi + pos_k, hh);
+        tcg::st_global(g_hk_lo + pos_k, hl);
+        const int64_t pos_mn = span + ((((lane >> 3) ^ (int)(row & 3))) << 3) + (lane & 7);
+        tcg::st_global(g_hmn_hi + pos_mn, hh);
+        tcg::st_global(g_hmn_lo + pos_mn, hl);
+      }
     }
   }
   if (threadIdx.x == 64) TCC_TRACE(5);
@@ -471,7 +534,7 @@ __global__ void __launch_bounds__(tcg::kThreads, 1) k_lstm_bwd_cluster(const BSt
           float old[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) old[q] = __ldcg(dp + q * H + u);
-          const float tc = tanhf(cn);
+          const float tc = ppb_cell_tanh(cn);
           const float dht = dh_head + v[g];
           const float dct = dc_next + dht * og * (1.0f - tc * tc);
           d[0] = dct * gg * ig * (1.0f - ig);

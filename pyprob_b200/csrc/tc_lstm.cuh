@@ -126,7 +126,7 @@ __device__ __forceinline__ void cell_epilogue(float* staging, const CellIO& io, 
 #pragma unroll
       for (int s = 0; s < 8; ++s)
         if (s < S) x = fmaf(__ldg(io.smp_emb + row * S + s), wsmp[s], x);
-      act = (g == 2) ? tanhf(x) : 1.0f / (1.0f + expf(-x));
+      act = (g == 2) ? ppb_cell_tanh(x) : ppb_cell_sigmoid(x);
     }
     tcg::st_global(io.gates + row * H4 + col, act);
     stg[r][lane] = act;
@@ -148,7 +148,7 @@ __device__ __forceinline__ void cell_epilogue(float* staging, const CellIO& io, 
       const int64_t rp = __ldg(io.row_prev + row);
       const float cp = tcg::ld_global(io.c + rp * H + u);
       cn = sg_f[r][lane] * cp + sg_i[r][lane] * sg_g[r][lane];
-      hn = sg_o[r][lane] * tanhf(cn);
+      hn = sg_o[r][lane] * ppb_cell_tanh(cn);
     }
     tcg::st_global(io.c + row * H + u, cn);
     tcg::st_global(io.h + row * H + u, hn);

@@ -28,6 +28,7 @@ st = torch.cuda.current_stream().cuda_stream
 loss = torch.empty((), device=dev); status = torch.zeros(1, dtype=torch.int32, device=dev)
 n = [0]
 def step():
+    st = torch.cuda.current_stream().cuda_stream
     grad.zero_()
     call('ppb_ic_loss_forward', net._handle, ptr(net._arena.data), C.byref(bs), ptr(net._workspace), need, prec, ptr(loss), ptr(status), None, 1, st)
     call('ppb_ic_loss_backward', net._handle, ptr(net._arena.data), ptr(grad), C.byref(bs), ptr(net._workspace), need, prec, 1.0, st)
@@ -57,15 +58,31 @@ call('ppb_debug_trace', ptr(tr))
 step()
 torch.cuda.synchronize()
 call('ppb_debug_trace', None)
-t = tr.cpu().numpy().reshape(NTR, 16)
-kinds = {0: 'grouped'}
-prev_end = None
-for i in range(NTR):
-    if t[i, 0] == 0: break
-    r = t[i]
-    kind = int(r[13]); name = 'grouped' if kind == 0 else ('cluster' if kind % 16 == 1 else 'lstm_cl') + 'x%d' % (kind // 16)
-    vis = (r[7] - r[0]) if r[7] else -1
-    print('tc launch %3d %-10s: M%5d N%5d K%5d grid%4d chunks%3d | setup %5d first_data %5d mma_issued %5d acc_ready %5d cluster_vis %5d epi_done %5d end %5d ns | start %+7d ns after previous end' % (
-        i, name, r[8], r[9], r[10], r[11], r[12], r[1]-r[0], r[2]-r[0], r[3]-r[0], r[4]-r[0], vis, r[5]-r[0], r[6]-r[0],
-        (r[0] - prev_end) if prev_end is not None else 0))
-    prev_end = r[6]
+def dump(t, title):
+    print(title)
+    prev_end = None
+    for i in range(NTR):
+        if t[i, 0] == 0: break
+        r = t[i]
+        kind = int(r[13]); name = 'grouped' if kind == 0 else ('cluster' if kind % 16 == 1 else 'lstm_cl') + 'x%d' % (kind // 16)
+        vis = (r[7] - r[0]) if r[7] else -1
+        print('tc launch %3d %-10s: M%5d N%5d K%5d grid%4d chunks%3d | setup %5d first_data %5d mma_issued %5d acc_ready %5d cluster_vis %5d loads_done %5d epi_done %5d end %5d ns | start %+7d ns after previous end' % (
+            i, name, r[8], r[9], r[10], r[11], r[12], r[1]-r[0], r[2]-r[0], r[3]-r[0], r[4]-r[0], vis, (r[14]-r[0]) if r[14] else -1, r[5]-r[0], r[6]-r[0],
+            (r[0] - prev_end) if prev_end is not None else 0))
+        prev_end = r[6]
+dump(tr.cpu().numpy().reshape(NTR, 16), '== eager launches')
+
+# the same step as one CUDA graph (the production form): the stamps of a replay show the gaps between dependent graph nodes
+tr.zero_()
+call('ppb_debug_trace', ptr(tr))
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    step()
+call('ppb_debug_trace', None)
+for _ in range(3): g.replay()
+torch.cuda.synchronize()
+e0.record()
+for _ in range(20): g.replay()
+e1.record(); torch.cuda.synchronize()
+print('graph replay: %.1f us per step' % (e0.elapsed_time(e1) * 1000 / 20))
+dump(tr.cpu().numpy().reshape(NTR, 16), '== graph replay (stamps of the last replay)')

@@ -88,7 +88,8 @@ def test_gemm_packed_tn(cuda, M, N, R, precision):
 
 
 @pytest.mark.parametrize('M,N,K,cs', [(128, 128, 64, 2), (512, 2048, 512, 2), (512, 512, 2048, 8), (256, 271, 512, 8),
-                                      (100, 70, 500, 4), (300, 96, 271, 4), (256, 30, 300, 2), (129, 257, 96, 2)])
+                                      (100, 70, 500, 4), (300, 96, 271, 4), (256, 30, 300, 2), (129, 257, 96, 2),
+                                      (256, 271, 30, 8), (128, 64, 40, 4)])   # K shorter than the cluster: empty splits
 @pytest.mark.parametrize('precision', [0, 1])
 def test_gemm_packed_cluster_split_k(cuda, M, N, K, cs, precision):
     """Cluster split-K (tc_cluster.cuh): the reduction of every output tile is divided over `cs` CTAs of one thread-block
