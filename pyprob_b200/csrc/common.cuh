@@ -40,6 +40,49 @@ extern unsigned long long g_ppb_launches;  // kernels launched by this library (
     }                                                                               \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------------------
+// A kernel launched with the programmatic-stream-serialisation attribute may START (block scheduling, shared-memory carve-out,
+// its own prologue) while its predecessor in the stream is still running; ppb_pdl_wait() then blocks until the predecessor
+// grid has completed and its writes are visible.  Between two dependent graph nodes the B200 leaves about 2 us idle
+// (profiles/r02d_phase_stamps_*: "start +2016 ns after previous end"), and the tensor-core kernels spend another ~1 us on
+// barrier init / TMEM allocation / descriptor fetch: both are hidden behind the predecessor's tail this way.
+// Rules kept by every converted kernel: before ppb_pdl_wait() it reads nothing but its host-uploaded descriptor table and
+// writes nothing to global memory; ppb_pdl_trigger() comes first so that the successor can be scheduled as early as possible
+// (the hardware launches it only after EVERY block of this grid has started, so it cannot starve this grid of SMs).
+// Both instructions are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void ppb_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void ppb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool ppb_pdl_enabled();   // default on; PPB_PDL=0 disables (lib.cu)
+
+// <<<grid, block, smem, st>>> with optional PDL attribute and optional (cluster, 1, 1) thread-block cluster
+template <typename... KArgs, typename... Args>
+inline cudaError_t ppb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                              int cluster, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl && ppb_pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = (unsigned)n;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 static inline int ppb_grid_for(int64_t n, int threads, int items_per_thread, int max_waves = 8) {
   int64_t blocks = (n + (int64_t)threads * items_per_thread - 1) / ((int64_t)threads * items_per_thread);
   if (blocks < 1) blocks = 1;

@@ -1,5 +1,6 @@
 // Library-wide plumbing: thread-local error string, version, device probe.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -12,6 +13,12 @@ void ppb_set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+// read at every launch (a getenv per eager launch; graph replays do not come here) so that tests can flip it in-process
+bool ppb_pdl_enabled() {
+  const char* e = getenv("PPB_PDL");
+  return !(e && e[0] == '0');
 }
 
 extern "C" {

@@ -438,6 +438,8 @@ __global__ void __launch_bounds__(256) k_cell_fwd(float* __restrict__ gates, con
                                                    const int* __restrict__ row_prev, const int* __restrict__ row_trace,
                                                    float* __restrict__ c, float* __restrict__ h, HImg himg, int row0,
                                                    int n_rows, int H, int S, int t) {
+  ppb_pdl_trigger();
+  ppb_pdl_wait();
   int64_t total = (int64_t)n_rows * H;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int i = (int)(e / H), j = (int)(e % H);
@@ -490,6 +492,8 @@ __global__ void __launch_bounds__(256) k_head_nll(const float* __restrict__ out_
                                                    int R, int K, float inv_batch, float* __restrict__ row_lp,
                                                    float* __restrict__ d_out, HImg dimg, float* __restrict__ loss_acc,
                                                    float* __restrict__ loss_out, int* __restrict__ status_out) {
+  ppb_pdl_trigger();
+  ppb_pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const int img_cols = (int)dimg.kb * 32;
@@ -652,12 +656,16 @@ __global__ void __launch_bounds__(256) k_head_nll(const float* __restrict__ out_
 
 // LSTM cell backward, one time step (reverse order).  dgates rows of this step are produced here;
 // dh_rec = dgates[t+1] W_hh (prefix of this step's rows), dc carries d c_t across steps.
-__global__ void __launch_bounds__(256) k_cell_bwd(const float* __restrict__ gates, const float* __restrict__ c,
+// 8 blocks of 256 threads per SM: the 1024 blocks of a 512-row, H = 512 step are ONE wave (at 40 registers it was 6 per SM,
+// a second wave of 136 blocks, and the kernel went from 9.2 to 10.7 us)
+__global__ void __launch_bounds__(256, 8) k_cell_bwd(const float* __restrict__ gates, const float* __restrict__ c,
                                                    const float* __restrict__ dh, const float* __restrict__ dh_rec,
                                                    float* __restrict__ dc, float* __restrict__ dgates,
                                                    float* __restrict__ d_pobs, const int* __restrict__ row_prev,
                                                    const int* __restrict__ row_next, const int* __restrict__ row_trace,
                                                    HImg gimg, int row0, int n_rows, int H, int t) {
+  ppb_pdl_trigger();
+  ppb_pdl_wait();
   // Index arithmetic once per (row, unit): the four gate columns j, H + j, 2H + j, 3H + j sit H / 32 column blocks apart
   // (H % 32 == 0 on this path), so their image positions differ by a constant; the kernel used to spend most of its
   // instructions on four independent 64-bit offset computations per format.
@@ -1432,6 +1440,8 @@ __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float
                                                float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
                                                float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
                                                float gscale) {
+  ppb_pdl_trigger();
+  ppb_pdl_wait();
   // torch.optim.Adam (no amsgrad): g += wd*p; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
   // p -= (lr / bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
   int64_t n4 = n >> 2;
@@ -1462,6 +1472,8 @@ __global__ void __launch_bounds__(256) k_adam_dev(float* __restrict__ p, const f
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n, int vec,
                                                    const float* __restrict__ hyper, long long* __restrict__ step_ctr,
                                                    float* __restrict__ bc1_out, unsigned int* __restrict__ done_ctr) {
+  ppb_pdl_trigger();
+  ppb_pdl_wait();
   __shared__ float s_bc[2];
   __shared__ long long s_t;
   if (threadIdx.x == 0) {
@@ -1735,9 +1747,8 @@ int ppb_adam_step(float* arena, const float* grad, float* exp_avg, float* exp_av
                   float beta2, float eps, float weight_decay, int64_t step, float grad_scale, void* stream) {
   PPB_CHECK_ARG(arena && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "bad arguments");
   double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-  k_adam<<<ppb_grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(arena, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
-                                                                   eps, weight_decay, (float)bc1, (float)sqrt(bc2),
-                                                                   grad_scale);
+  PPB_CUDA(ppb_launch(k_adam, dim3(ppb_grid_for(n, 256, 4)), dim3(256), 0, (cudaStream_t)stream, true, 0, arena, grad, exp_avg,
+                      exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale));
   PPB_LAUNCH_CHECK();
   return PPB_OK;
 }
@@ -1750,9 +1761,9 @@ int ppb_adam_step_dev(float* arena, const float* grad, float* exp_avg, float* ex
                       const float* hyper_dev, void* state_dev, void* stream) {
   PPB_CHECK_ARG(arena && grad && exp_avg && exp_avg_sq && hyper_dev && state_dev && n > 0, "bad arguments");
   const int vec = ((((uintptr_t)arena | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0) ? 1 : 0;
-  k_adam_dev<<<ppb_grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(
-      arena, grad, exp_avg, exp_avg_sq, n, vec, hyper_dev, (long long*)state_dev, (float*)((char*)state_dev + 8),
-      (unsigned int*)((char*)state_dev + 12));
+  PPB_CUDA(ppb_launch(k_adam_dev, dim3(ppb_grid_for(n, 256, 4)), dim3(256), 0, (cudaStream_t)stream, true, 0, arena, grad,
+                      exp_avg, exp_avg_sq, n, vec, hyper_dev, (long long*)state_dev, (float*)((char*)state_dev + 8),
+                      (unsigned int*)((char*)state_dev + 12)));
   PPB_LAUNCH_CHECK();
   return PPB_OK;
 }

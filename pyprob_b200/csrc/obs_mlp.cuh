@@ -344,6 +344,8 @@ __device__ __forceinline__ void warp_dense_dx(const float* dy, int out_dim, cons
 // backward chain per trace: fills the d(pre-activation) buffers of every layer (no weight gradients here)
 __global__ void __launch_bounds__(kWarps * 32) k_bwd2_dx(Net net, const float* __restrict__ arena, int B, int traces_per_cta,
                                                          Bufs bufs, DBufs dbufs) {
+  ppb_pdl_trigger();
+  ppb_pdl_wait();
   extern __shared__ float smem[];
   float* p = smem;
   const float* w_obs[PPB_MAX_OBS][PPB_MAX_FF_LAYERS];
@@ -409,6 +411,8 @@ struct DwTable { int n_layers, total; DwLayer layer[PPB_MAX_OBS * PPB_MAX_FF_LAY
 // block = 8 warps x 32 consecutive gradient entries: lane = entry, the warps stride over the traces of the block's slice,
 // partial sums meet in shared memory (every thread runs B / 8 iterations, not B)
 __global__ void __launch_bounds__(256) k_dw(DwTable tab, int B, int b_chunk, float* __restrict__ grad) {
+  ppb_pdl_trigger();
+  ppb_pdl_wait();
   __shared__ float part[8][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int idx = blockIdx.x * 32 + lane;

@@ -106,7 +106,7 @@ inline size_t smem_bytes() { return sizeof(Smem) + 1024; }
 template <bool X3>
 __device__ __forceinline__ void mainloop_and_park(Smem& sm, const tcg::Operand& A, const tcg::Operand& B, int mt, int nt,
                                                   int c0, int c1, uint32_t tmem, int warp, int lane,
-                                                  unsigned long long* trace = nullptr) {
+                                                  unsigned long long* trace = nullptr, int b_prefetched = 0) {
   if (warp == 0) {
     if (lane == 0) {
       const uint32_t bytes = (tcg::stage_bytes(A, mt) + tcg::stage_bytes(B, nt)) * (X3 ? 2u : 1u);
@@ -114,9 +114,10 @@ __device__ __forceinline__ void mainloop_and_park(Smem& sm, const tcg::Operand& 
         int s = (c - c0) % tcg::kStages;
         uint32_t ph = ((c - c0) / tcg::kStages) & 1;
         mbar_wait(&sm.empty[s], ph ^ 1);
-        mbar_expect_tx(&sm.full[s], bytes);
+        const bool b_there = c - c0 < b_prefetched;   // B tile (and the expect-tx) of this stage issued before the PDL wait
+        if (!b_there) mbar_expect_tx(&sm.full[s], bytes);
         tcg::load_operand(A, mt, c, sm.a_hi[s], sm.a_lo[s], X3, &sm.full[s]);
-        tcg::load_operand(B, nt, c, sm.b_hi[s], sm.b_lo[s], X3, &sm.full[s]);
+        if (!b_there) tcg::load_operand(B, nt, c, sm.b_hi[s], sm.b_lo[s], X3, &sm.full[s]);
       }
     }
   } else if (warp == 1) {
@@ -202,7 +203,7 @@ __device__ __forceinline__ void reduce_row(const Smem& sm, int row, int lane, fl
   }
 }
 
-__device__ __forceinline__ void common_setup(Smem& sm, int warp, int lane) {
+__device__ __forceinline__ void common_setup(Smem& sm, int warp, int lane, bool pdl_wait = true) {
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < tcg::kStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
     mbar_init(&sm.tmem_full, 1);
@@ -212,6 +213,9 @@ __device__ __forceinline__ void common_setup(Smem& sm, int warp, int lane) {
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
+  // PDL (common.cuh): up to here only the host-uploaded descriptor table, shared memory and TMEM were touched
+  ppb_pdl_trigger();
+  if (pdl_wait) ppb_pdl_wait();
 }
 
 // ---- generic flavours -------------------------------------------------------------------------------------------------
@@ -358,13 +362,38 @@ __global__ void __launch_bounds__(tcg::kThreads, 1) k_lstm_cluster(const tcl::St
   const int mt = local / P.tiles_n, nt = local % P.tiles_n;   // nt = block of 32 hidden units
   const int KC = (io.H + 31) / 32;
   const int c0 = (int)((int64_t)KC * split / CS), c1 = (int)((int64_t)KC * (split + 1) / CS);
-  common_setup(sm, warp, lane);
+  common_setup(sm, warp, lane, false);
   const uint32_t tmem = sm.tmem_base;
   if (threadIdx.x == 0) TCC_TRACE(1);
-  mainloop_and_park<X3>(sm, P.a, P.b, mt, nt, c0, c1, tmem, warp, lane, trace);
+  // The W_hh tiles of the first stages do not depend on the previous time step (the images are packed once per training step,
+  // before the chain of step kernels starts): the producer requests them BEFORE the PDL wait, so that only the h_{t-1} tiles
+  // remain to be fetched once the previous step's kernel has finished.
+  int b_pre = 0;
+  if (warp == 0 && lane == 0) {
+    const uint32_t bytes = (tcg::stage_bytes(P.a, mt) + tcg::stage_bytes(P.b, nt)) * (X3 ? 2u : 1u);
+    b_pre = (c1 - c0) < tcg::kStages ? (c1 - c0) : tcg::kStages;
+    for (int i = 0; i < b_pre; ++i) {
+      mbar_expect_tx(&sm.full[i], bytes);
+      tcg::load_operand(P.b, nt, c0 + i, sm.b_hi[i], sm.b_lo[i], X3, &sm.full[i]);
+    }
+  }
+  ppb_pdl_wait();
+  // Row metadata of this warp's rows (trace, step, previous row): it heads the dependency chain of the whole epilogue, so the
+  // epilogue warps fetch it while the mainloop runs instead of after the cluster barrier.
+  constexpr int kRowsPerCta = 128 / CS, kRowsPerWarp = kRowsPerCta / tcg::kEpiWarps;
+  int m_tr[kRowsPerWarp], m_st[kRowsPerWarp], m_rp[kRowsPerWarp];
+  if (warp >= 2) {
+#pragma unroll
+    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+      const int64_t row = (int64_t)P.row0 + mt * 128 + split * kRowsPerCta + (warp - 2) * kRowsPerWarp + rr;
+      m_tr[rr] = __ldg(io.row_trace + row);
+      m_st[rr] = __ldg(io.row_step + row);
+      m_rp[rr] = (int)__ldg(io.row_prev + row);
+    }
+  }
+  mainloop_and_park<X3>(sm, P.a, P.b, mt, nt, c0, c1, tmem, warp, lane, trace, b_pre);
 
   if (warp >= 2) {
-    constexpr int kRowsPerCta = 128 / CS, kRowsPerWarp = kRowsPerCta / tcg::kEpiWarps;
     const int ew = warp - 2;
     const int H = io.H, H4 = 4 * io.H, S = io.S;
     const int u = nt * 32 + lane;     // hidden unit of this lane
@@ -374,16 +403,6 @@ __global__ void __launch_bounds__(tcg::kThreads, 1) k_lstm_cluster(const tcl::St
 #pragma unroll
       for (int s = 0; s < SMAX; ++s) wsmp[g][s] = (s < S) ? __ldg(io.w_smp_t + (int64_t)s * H4 + g * H + u) : 0.0f;
     const int64_t hkb = io.hkb;
-    // row metadata of all this warp's rows first: it heads every row's dependency chain
-    int m_tr[kRowsPerWarp], m_st[kRowsPerWarp];
-    int64_t m_rp[kRowsPerWarp];
-#pragma unroll
-    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
-      const int64_t row = (int64_t)P.row0 + mt * 128 + split * kRowsPerCta + ew * kRowsPerWarp + rr;
-      m_tr[rr] = __ldg(io.row_trace + row);
-      m_st[rr] = __ldg(io.row_step + row);
-      m_rp[rr] = __ldg(io.row_prev + row);
-    }
     // Two passes over the warp's rows.  Pass 1 holds no stores (and no compiler barrier), so the loads of all rows — partial
     // sums from the peers' shared memory, P_obs / P_step / c_{t-1} from L2 — are in flight together instead of one row's
     // latency chain after the other; pass 2 writes the results.
@@ -400,7 +419,7 @@ __global__ void __launch_bounds__(tcg::kThreads, 1) k_lstm_cluster(const tcl::St
         const bool live = m_tr[rr] >= 0;
         const int64_t row = live ? seg_row0 + mt * 128 + trow : seg_row0;     // global row of the step (a valid one)
         const int tr = live ? m_tr[rr] : 0, st = live ? m_st[rr] : 0;
-        const int64_t rp = (live && m_rp[rr] >= 0) ? m_rp[rr] : 0;
+        const int64_t rp = (live && m_rp[rr] >= 0) ? (int64_t)m_rp[rr] : 0;
         float v[4];
         reduce_row<CS>(sm, trow, lane, v);
         float sm_e[SMAX];
@@ -567,22 +586,10 @@ __global__ void __launch_bounds__(tcg::kThreads, 1) k_lstm_bwd_cluster(const BSt
   }
 }
 
-// host-side launch with a (CS, 1, 1) cluster
+// host-side launch with a (CS, 1, 1) cluster (and the PDL attribute, common.cuh)
 template <typename Kernel, typename... Args>
 inline cudaError_t launch_cluster(Kernel kernel, int grid, int cluster, size_t smem, cudaStream_t st, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid, 1, 1);
-  cfg.blockDim = dim3(tcg::kThreads, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)cluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, args...);
+  return ppb_launch(kernel, dim3((unsigned)grid, 1, 1), dim3(tcg::kThreads, 1, 1), smem, st, true, cluster, args...);
 }
 
 }  // namespace tcc

@@ -160,6 +160,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_grouped(const Problem* __restri
   fence_after_sync();
   const uint32_t tmem = sm.tmem_base;
   if (threadIdx.x == 0) TCG_TRACE(1);
+  // PDL (common.cuh): everything above touched only the host-uploaded descriptor table, shared memory and TMEM
+  ppb_pdl_trigger();
+  ppb_pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
