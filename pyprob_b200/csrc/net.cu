@@ -658,12 +658,15 @@ __global__ void __launch_bounds__(256) k_head_nll(const float* __restrict__ out_
 // dh_rec = dgates[t+1] W_hh (prefix of this step's rows), dc carries d c_t across steps.
 // 8 blocks of 256 threads per SM: the 1024 blocks of a 512-row, H = 512 step are ONE wave (at 40 registers it was 6 per SM,
 // a second wave of 136 blocks, and the kernel went from 9.2 to 10.7 us)
-__global__ void __launch_bounds__(256, 8) k_cell_bwd(const float* __restrict__ gates, const float* __restrict__ c,
+// FINAL (the t = 0 launch, which ends every trace's sum): the per-trace gradient d_pobs is also written as tile images
+// (pimg), so that no packing kernel sits between BPTT and the weight-gradient GEMMs.
+template <bool FINAL>
+__global__ void __launch_bounds__(256, FINAL ? 4 : 8) k_cell_bwd(const float* __restrict__ gates, const float* __restrict__ c,
                                                    const float* __restrict__ dh, const float* __restrict__ dh_rec,
                                                    float* __restrict__ dc, float* __restrict__ dgates,
                                                    float* __restrict__ d_pobs, const int* __restrict__ row_prev,
                                                    const int* __restrict__ row_next, const int* __restrict__ row_trace,
-                                                   HImg gimg, int row0, int n_rows, int H, int t) {
+                                                   HImg gimg, int row0, int n_rows, int H, int t, HImg pimg) {
   ppb_pdl_trigger();
   ppb_pdl_wait();
   // Index arithmetic once per (row, unit): the four gate columns j, H + j, 2H + j, 3H + j sit H / 32 column blocks apart
@@ -695,12 +698,25 @@ __global__ void __launch_bounds__(256, 8) k_cell_bwd(const float* __restrict__ g
       dv[3] = dht * tc_ * og * (1.0f - og);
       dc[rH] = dct * fg;
       float* dp = d_pobs + (int64_t)tr * 4 * H + j;
-      if (has_next) {
+      float tot[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) dp[q * H] += dv[q];
-      } else {
+      for (int q = 0; q < 4; ++q) {
+        tot[q] = has_next ? dp[q * H] + dv[q] : dv[q];
+        dp[q * H] = tot[q];
+      }
+      if (FINAL && pimg.k_hi) {   // H % 32 == 0 on this path: the gate blocks sit gate_stride apart in the image as well
+        const int64_t pk = tc::packed_offset(tr, j, pimg.kb), pmn = tc::packed_offset_mn(tr, j, pimg.kb);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) dp[q * H] = dv[q];
+        for (int q = 0; q < 4; ++q) {
+          float hi, lo;
+          tc::split_tf32(tot[q], hi, lo);
+          pimg.k_hi[pk + q * gate_stride] = hi;
+          if (pimg.k_lo) pimg.k_lo[pk + q * gate_stride] = lo;
+          if (pimg.mn_hi) {
+            pimg.mn_hi[pmn + q * gate_stride] = hi;
+            if (pimg.mn_lo) pimg.mn_lo[pmn + q * gate_stride] = lo;
+          }
+        }
       }
     }
 #pragma unroll
@@ -1377,8 +1393,8 @@ int ppb_ic_loss_backward(ppb_net* net, const float* arena, float* grad, const pp
     int r0 = b->row_off_host[t], n = b->row_off_host[t + 1] - r0;
     int n_next = (t + 1 < d.T) ? b->row_off_host[t + 2] - b->row_off_host[t + 1] : 0;
     if (n_next > 0) { rc = run_phase(bl.phases[ph_rec0 + (d.T - 2 - t)], dprobs, st, &bl); if (rc) return rc; }
-    k_cell_bwd<<<ew_grid((int64_t)n * H), 256, 0, st>>>(w.gates, w.c, w.dh, w.dh_rec, w.dc, dgates, w.d_pobs, b->row_prev,
-                                                       b->row_next, b->row_trace, HImg(), r0, n, H, t);
+    k_cell_bwd<false><<<ew_grid((int64_t)n * H), 256, 0, st>>>(w.gates, w.c, w.dh, w.dh_rec, w.dc, dgates, w.d_pobs, b->row_prev,
+                                                       b->row_next, b->row_trace, HImg(), r0, n, H, t, HImg());
     PPB_LAUNCH_CHECK();
   }
   {
@@ -1747,7 +1763,7 @@ int ppb_adam_step(float* arena, const float* grad, float* exp_avg, float* exp_av
                   float beta2, float eps, float weight_decay, int64_t step, float grad_scale, void* stream) {
   PPB_CHECK_ARG(arena && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "bad arguments");
   double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-  PPB_CUDA(ppb_launch(k_adam, dim3(ppb_grid_for(n, 256, 4)), dim3(256), 0, (cudaStream_t)stream, true, 0, arena, grad, exp_avg,
+  PPB_CUDA(ppb_launch(k_adam, dim3(ppb_grid_for(n, 256, 4)), dim3(256), 0, (cudaStream_t)stream, 2, 0, arena, grad, exp_avg,
                       exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale));
   PPB_LAUNCH_CHECK();
   return PPB_OK;
@@ -1761,7 +1777,7 @@ int ppb_adam_step_dev(float* arena, const float* grad, float* exp_avg, float* ex
                       const float* hyper_dev, void* state_dev, void* stream) {
   PPB_CHECK_ARG(arena && grad && exp_avg && exp_avg_sq && hyper_dev && state_dev && n > 0, "bad arguments");
   const int vec = ((((uintptr_t)arena | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0) ? 1 : 0;
-  PPB_CUDA(ppb_launch(k_adam_dev, dim3(ppb_grid_for(n, 256, 4)), dim3(256), 0, (cudaStream_t)stream, true, 0, arena, grad,
+  PPB_CUDA(ppb_launch(k_adam_dev, dim3(ppb_grid_for(n, 256, 4)), dim3(256), 0, (cudaStream_t)stream, 2, 0, arena, grad,
                       exp_avg, exp_avg_sq, n, vec, hyper_dev, (long long*)state_dev, (float*)((char*)state_dev + 8),
                       (unsigned int*)((char*)state_dev + 12)));
   PPB_LAUNCH_CHECK();

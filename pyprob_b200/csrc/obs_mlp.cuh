@@ -4,6 +4,7 @@
 // wide / large-batch cases fall back to the grouped GEMM path.
 #pragma once
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace obsmlp {
 
@@ -18,6 +19,10 @@ struct Bufs {  // global activation buffers (forward writes, backward reads) —
   float* obs_cat;
   float* fin_act[PPB_MAX_FF_LAYERS];
   float* obs_emb;
+  // optional: tf32 tile images of obs_emb (tc.cuh), written by k_fwd2 itself so that no packing kernel sits between the
+  // embedding and the P_obs GEMM on the critical path (only when B % 128 == 0 and E % 32 == 0: no padding to zero-fill)
+  float* emb_k_hi = nullptr; float* emb_k_lo = nullptr; float* emb_mn_hi = nullptr; float* emb_mn_lo = nullptr;
+  long long emb_kb = 0;
 };
 
 struct Net {
@@ -310,6 +315,20 @@ __global__ void __launch_bounds__(kWarps * 32) k_fwd2(Net net, const float* __re
       warp_dense_fwd(cur, L.in_dim, w_fin[l], L.out_dim, nxt, 0,
                      (last ? bufs.obs_emb : bufs.fin_act[l]) + (int64_t)tr * L.out_dim, lane);
       float* t = cur; cur = nxt; nxt = (t == cat) ? vb : t;
+    }
+    if (bufs.emb_k_hi) {   // cur = the embedding of this trace (warp-private shared memory)
+      for (int k = lane; k < net.E; k += 32) {
+        float hi, lo;
+        tc::split_tf32(cur[k], hi, lo);
+        const int64_t ok = tc::packed_offset(tr, k, bufs.emb_kb);
+        bufs.emb_k_hi[ok] = hi;
+        if (bufs.emb_k_lo) bufs.emb_k_lo[ok] = lo;
+        if (bufs.emb_mn_hi) {
+          const int64_t om = tc::packed_offset_mn(tr, k, bufs.emb_kb);
+          bufs.emb_mn_hi[om] = hi;
+          if (bufs.emb_mn_lo) bufs.emb_mn_lo[om] = lo;
+        }
+      }
     }
     __syncwarp();
   }

@@ -372,6 +372,7 @@ __global__ void __launch_bounds__(tcg::kThreads, 1) k_lstm_cluster(const tcl::St
   if (warp == 0 && lane == 0) {
     const uint32_t bytes = (tcg::stage_bytes(P.a, mt) + tcg::stage_bytes(P.b, nt)) * (X3 ? 2u : 1u);
     b_pre = (c1 - c0) < tcg::kStages ? (c1 - c0) : tcg::kStages;
+    if (P.io.no_b_prefetch) b_pre = 0;
     for (int i = 0; i < b_pre; ++i) {
       mbar_expect_tx(&sm.full[i], bytes);
       tcg::load_operand(P.b, nt, c0 + i, sm.b_hi[i], sm.b_lo[i], X3, &sm.full[i]);
@@ -514,66 +515,91 @@ __global__ void __launch_bounds__(tcg::kThreads, 1) k_lstm_bwd_cluster(const BSt
   const int c0 = (int)((int64_t)KC * split / CS), c1 = (int)((int64_t)KC * (split + 1) / CS);
   common_setup(sm, warp, lane);
   const uint32_t tmem = sm.tmem_base;
+  // row metadata while the mainloop runs (it heads the dependency chain of the reduce phase)
+  constexpr int kRowsPerCta = 128 / CS, kRowsPerWarp = kRowsPerCta / tcg::kEpiWarps;
+  int m_tr[kRowsPerWarp], m_nx[kRowsPerWarp], m_rp[kRowsPerWarp];
+  if (warp >= 2) {
+#pragma unroll
+    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+      const int64_t row = (int64_t)P.row0 + mt * 128 + split * kRowsPerCta + (warp - 2) * kRowsPerWarp + rr;
+      m_tr[rr] = __ldg(io.row_trace + row);
+      m_nx[rr] = __ldg(io.row_next + row);
+      m_rp[rr] = (P.t > 0) ? __ldg(io.row_prev + row) : 0;
+    }
+  }
   mainloop_and_park<X3>(sm, P.a, P.b, mt, nt, c0, c1, tmem, warp, lane);
 
   if (warp >= 2) {
-    constexpr int kRowsPerCta = 128 / CS, kRowsPerWarp = kRowsPerCta / tcg::kEpiWarps;
     const int ew = warp - 2;
+    // descriptor fields in registers (P sits in shared memory behind a generic pointer, every io.x would be a dependent load)
+    const float* const g_gates = io.gates; const float* const g_c = io.c; const float* const g_dh = io.dh;
+    float* const g_dc = io.dc; float* const g_dp = io.d_pobs; float* const g_dg = io.dgates;
+    float* const gk_hi = io.gk_hi; float* const gk_lo = io.gk_lo; float* const gmn_hi = io.gmn_hi; float* const gmn_lo = io.gmn_lo;
     const int64_t gkb = io.gkb;
+    const bool has_prev = P.t > 0;
+    const int64_t seg_row0 = (int64_t)P.row0;
+    const int n_blocks = (H - nt * 128 + 31) >> 5;     // 32-unit blocks of this tile inside H (warp-uniform)
 #pragma unroll
     for (int rr = 0; rr < kRowsPerWarp; ++rr) {
       const int trow = split * kRowsPerCta + ew * kRowsPerWarp + rr;
-      const int64_t row = (int64_t)P.row0 + mt * 128 + trow;
-      const int tr = __ldg(io.row_trace + row);
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      int64_t nx = 0, rp = 0;
-      if (tr >= 0) {   // warp-uniform
-        reduce_row<CS>(sm, trow, lane, v);
-        nx = __ldg(io.row_next + row);
-        rp = (P.t > 0) ? __ldg(io.row_prev + row) : 0;
+      const int64_t row = seg_row0 + mt * 128 + trow;
+      const bool live = m_tr[rr] >= 0;
+      // pass 1 — ONE basic block: partial sums from the peers' shared memory and every element-wise operand of the row's four
+      // unit blocks in flight together; padding rows / unit blocks beyond H read a valid address and are zeroed afterwards
+      const int64_t lrow = live ? row : seg_row0;
+      const int64_t ltr = live ? m_tr[rr] : 0, lnx = (live && m_nx[rr] >= 0) ? m_nx[rr] : 0, lrp = live ? m_rp[rr] : 0;
+      float v[4];
+      reduce_row<CS>(sm, trow, lane, v);
+      float d[4][4], dcf[4], pob[4][4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int u = (g < n_blocks) ? nt * 128 + g * 32 + lane : lane;
+        const float* gr = g_gates + lrow * H4 + u;
+        const float* dp = g_dp + ltr * H4 + u;
+        const float ig = __ldg(gr), fg = __ldg(gr + H), gg = __ldg(gr + 2 * H), og = __ldg(gr + 3 * H);
+        const float cn = __ldg(g_c + lrow * H + u);
+        const float cpv = __ldg(g_c + lrp * H + u);
+        const float dh_head = __ldg(g_dh + lrow * H + u);
+        const float dc_next = __ldcg(g_dc + lnx * H + u);
+        float old[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) old[q] = __ldcg(dp + q * H);
+        const float cp = has_prev ? cpv : 0.0f;
+        const float tc = ppb_cell_tanh(cn);
+        const float dht = dh_head + v[g];
+        const float dct = (m_nx[rr] >= 0 ? dc_next : 0.0f) + dht * og * (1.0f - tc * tc);
+        d[g][0] = live ? dct * gg * ig * (1.0f - ig) : 0.0f;
+        d[g][1] = live ? dct * cp * fg * (1.0f - fg) : 0.0f;
+        d[g][2] = live ? dct * ig * (1.0f - gg * gg) : 0.0f;
+        d[g][3] = live ? dht * tc * og * (1.0f - og) : 0.0f;
+        dcf[g] = dct * fg;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pob[g][q] = old[q] + d[g][q];
       }
+      // pass 2 — stores
       const int64_t img_row = ((row >> 7) * gkb) * kTileFloats + (row & 127) * 32;
       const int pk = ((((lane >> 2) ^ (int)(row & 7))) << 2) + (lane & 3);
       const int pmn = ((((lane >> 3) ^ (int)(row & 3))) << 3) + (lane & 7);
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
+        if (g >= n_blocks) continue;   // warp-uniform: unit block beyond H (H < 128 * tiles_n)
         const int u = nt * 128 + g * 32 + lane;
-        if (u - lane >= H) continue;   // warp-uniform: unit block beyond H (H < 128 * tiles_n)
-        float d[4] = {0.f, 0.f, 0.f, 0.f};
-        if (tr >= 0) {
-          // every operand of this (row, unit) in flight at once: plain (non-volatile) loads, one L2 round trip — the
-          // read-modify-write of d_pobs used to be four dependent round trips per unit
-          const float* gr = io.gates + row * H4;
-          float* dp = io.d_pobs + (int64_t)tr * H4;
-          const float ig = __ldg(gr + u), fg = __ldg(gr + H + u), gg = __ldg(gr + 2 * H + u), og = __ldg(gr + 3 * H + u);
-          const float cn = __ldg(io.c + row * H + u);
-          const float cp = (P.t > 0) ? __ldg(io.c + rp * H + u) : 0.0f;
-          const float dh_head = __ldg(io.dh + row * H + u);
-          const float dc_next = __ldcg(io.dc + nx * H + u);
-          float old[4];
+        if (live) {
+          tcg::st_global(g_dc + row * H + u, dcf[g]);
+          float* dp = g_dp + (int64_t)m_tr[rr] * H4 + u;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) old[q] = __ldcg(dp + q * H + u);
-          const float tc = ppb_cell_tanh(cn);
-          const float dht = dh_head + v[g];
-          const float dct = dc_next + dht * og * (1.0f - tc * tc);
-          d[0] = dct * gg * ig * (1.0f - ig);
-          d[1] = dct * cp * fg * (1.0f - fg);
-          d[2] = dct * ig * (1.0f - gg * gg);
-          d[3] = dht * tc * og * (1.0f - og);
-          tcg::st_global(io.dc + row * H + u, dct * fg);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) tcg::st_global(dp + q * H + u, old[q] + d[q]);
+          for (int q = 0; q < 4; ++q) tcg::st_global(dp + q * H, pob[g][q]);
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          tcg::st_global(io.dgates + row * H4 + q * H + u, d[q]);
+          tcg::st_global(g_dg + row * H4 + q * H + u, d[g][q]);
           const int64_t span = img_row + (int64_t)((q * H + u - lane) >> 5) * kTileFloats;
           float hh, hl;
-          split_tf32(d[q], hh, hl);
-          tcg::st_global(io.gk_hi + span + pk, hh);
-          tcg::st_global(io.gk_lo + span + pk, hl);
-          tcg::st_global(io.gmn_hi + span + pmn, hh);
-          tcg::st_global(io.gmn_lo + span + pmn, hl);
+          split_tf32(d[g][q], hh, hl);
+          tcg::st_global(gk_hi + span + pk, hh);
+          tcg::st_global(gk_lo + span + pk, hl);
+          tcg::st_global(gmn_hi + span + pmn, hh);
+          tcg::st_global(gmn_lo + span + pmn, hl);
         }
       }
     }
@@ -589,7 +615,7 @@ __global__ void __launch_bounds__(tcg::kThreads, 1) k_lstm_bwd_cluster(const BSt
 // host-side launch with a (CS, 1, 1) cluster (and the PDL attribute, common.cuh)
 template <typename Kernel, typename... Args>
 inline cudaError_t launch_cluster(Kernel kernel, int grid, int cluster, size_t smem, cudaStream_t st, Args... args) {
-  return ppb_launch(kernel, dim3((unsigned)grid, 1, 1), dim3(tcg::kThreads, 1, 1), smem, st, true, cluster, args...);
+  return ppb_launch(kernel, dim3((unsigned)grid, 1, 1), dim3(tcg::kThreads, 1, 1), smem, st, 1, cluster, args...);
 }
 
 }  // namespace tcc

@@ -37,6 +37,7 @@ struct CellIO {               // element-wise operands of the cell update, share
   float* hk_hi; float* hk_lo; float* hmn_hi; float* hmn_lo;   // tile images of h (both formats)
   int hkb;                    // column blocks of the h images (H / 32)
   int H, S;                   // hidden size (reduction length; N = 4H), sample-embedding width (<= 8)
+  int no_b_prefetch;          // 1: the cluster kernel does not request W_hh tiles ahead of its PDL wait (A/B switch)
 };
 
 struct Step {                 // one (time step t >= 1, sub-batch) segment: one launch per time step

@@ -41,6 +41,20 @@ e0.record()
 for _ in range(50): step()
 e1.record(); torch.cuda.synchronize()
 print('avg step (no L2 flush, back-to-back): %.1f us  | rows %d params %d' % (e0.elapsed_time(e1) * 1000 / 50, enc.n_rows, net._arena.numel()))
+if len(sys.argv) > 4 and sys.argv[4] == 'quick':   # A/B mode: eager and graph-replay step time only
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        step()
+    for _ in range(5): g.replay()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(5):
+        e0.record()
+        for _ in range(20): g.replay()
+        e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) * 1000 / 20)
+    print('graph replay: %.1f us per step (best of 5 x 20)' % best)
+    sys.exit(0)
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(5): step()
