@@ -1492,6 +1492,18 @@ __global__ void __launch_bounds__(256) k_adam_dev(float* __restrict__ p, const f
   ppb_pdl_wait();
   __shared__ float s_bc[2];
   __shared__ long long s_t;
+  // the gradient / moment loads of the first pass are issued BEFORE the block waits for thread 0's two double-precision
+  // pow() calls (the bias corrections used to sit in front of every block's first load)
+  const int64_t n4 = vec ? (n >> 2) : 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 gg = z4, mm = z4, vv = z4;
+  if (q < n4) {
+    gg = reinterpret_cast<const float4*>(g)[q];
+    mm = reinterpret_cast<float4*>(m)[q];
+    vv = reinterpret_cast<float4*>(v)[q];
+  }
   if (threadIdx.x == 0) {
     long long t = *step_ctr + 1;
     s_t = t;
@@ -1501,23 +1513,28 @@ __global__ void __launch_bounds__(256) k_adam_dev(float* __restrict__ p, const f
   __syncthreads();
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], gscale = hyper[5];
   const float step = lr / s_bc[0], bc2_sqrt = s_bc[1];
-  const int64_t n4 = vec ? (n >> 2) : 0;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
-    float4 gg = reinterpret_cast<const float4*>(g)[q];
-    float4 mm = reinterpret_cast<float4*>(m)[q], vv = reinterpret_cast<float4*>(v)[q];
+  while (q < n4) {
     // a tensor that has never seen a gradient (g = m = v = 0) and no weight decay: the update is exactly zero — skip
     // the parameter read and all three writes (T = 1 models never touch W_hh: 64 % of the configs[1] arena)
-    if (wd == 0.0f && gg.x == 0.0f && gg.y == 0.0f && gg.z == 0.0f && gg.w == 0.0f && mm.x == 0.0f && mm.y == 0.0f &&
-        mm.z == 0.0f && mm.w == 0.0f && vv.x == 0.0f && vv.y == 0.0f && vv.z == 0.0f && vv.w == 0.0f)
-      continue;
-    float4 pp = reinterpret_cast<float4*>(p)[q];
-    ppb_adam_update(pp.x, gg.x, mm.x, vv.x, b1, b2, eps, wd, gscale, step, bc2_sqrt);
-    ppb_adam_update(pp.y, gg.y, mm.y, vv.y, b1, b2, eps, wd, gscale, step, bc2_sqrt);
-    ppb_adam_update(pp.z, gg.z, mm.z, vv.z, b1, b2, eps, wd, gscale, step, bc2_sqrt);
-    ppb_adam_update(pp.w, gg.w, mm.w, vv.w, b1, b2, eps, wd, gscale, step, bc2_sqrt);
-    reinterpret_cast<float4*>(p)[q] = pp;
-    reinterpret_cast<float4*>(m)[q] = mm;
-    reinterpret_cast<float4*>(v)[q] = vv;
+    const bool zero = wd == 0.0f && gg.x == 0.0f && gg.y == 0.0f && gg.z == 0.0f && gg.w == 0.0f && mm.x == 0.0f &&
+                      mm.y == 0.0f && mm.z == 0.0f && mm.w == 0.0f && vv.x == 0.0f && vv.y == 0.0f && vv.z == 0.0f &&
+                      vv.w == 0.0f;
+    if (!zero) {
+      float4 pp = reinterpret_cast<float4*>(p)[q];
+      ppb_adam_update(pp.x, gg.x, mm.x, vv.x, b1, b2, eps, wd, gscale, step, bc2_sqrt);
+      ppb_adam_update(pp.y, gg.y, mm.y, vv.y, b1, b2, eps, wd, gscale, step, bc2_sqrt);
+      ppb_adam_update(pp.z, gg.z, mm.z, vv.z, b1, b2, eps, wd, gscale, step, bc2_sqrt);
+      ppb_adam_update(pp.w, gg.w, mm.w, vv.w, b1, b2, eps, wd, gscale, step, bc2_sqrt);
+      reinterpret_cast<float4*>(p)[q] = pp;
+      reinterpret_cast<float4*>(m)[q] = mm;
+      reinterpret_cast<float4*>(v)[q] = vv;
+    }
+    q += stride;
+    if (q < n4) {
+      gg = reinterpret_cast<const float4*>(g)[q];
+      mm = reinterpret_cast<float4*>(m)[q];
+      vv = reinterpret_cast<float4*>(v)[q];
+    }
   }
   for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {

@@ -66,9 +66,19 @@ struct Sink {
 };
 
 // ---- two-parameter families ---------------------------------------------------------------------
+// MUFU approximations (<= 2 ulp): the scoring kernels are bound by instruction issue, not HBM, as soon as they carry an IEEE
+// division or a libm logf/expf (ncu: profiles/r02c_ncu_scoring.md); results stay within 1e-6 relative of the libm forms.
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 struct NormalOp {
   static constexpr bool kTable = false;
-  __device__ __forceinline__ float operator()(float v, float a, float b, const float*) const { return ppb_normal_lp(v, a, b); }
+  // torch/distributions/normal.py log_prob: -((v - mu)^2) / (2 var) - log(sigma) - log(sqrt(2 pi))
+  __device__ __forceinline__ float operator()(float v, float mu, float sigma, const float*) const {
+    const float z = (v - mu) * fast_rcp(sigma);
+    return fmaf(-0.5f * z, z, -fast_lg2(sigma) * PPB_LN2) - PPB_LOG_SQRT_2PI;
+  }
 };
 struct UniformOp {
   // torch/distributions/uniform.py log_prob: log(lb*ub) - log(high-low), lb = low<=v, ub = high>v
@@ -87,7 +97,7 @@ struct PoissonOp {
   static constexpr bool kTable = true;
   // torch/distributions/poisson.py log_prob: xlogy(v, rate) - rate - lgamma(v+1)
   __device__ __forceinline__ float operator()(float v, float rate, float, const float* tab) const {
-    float xl = (v == 0.0f) ? 0.0f : v * logf(rate);
+    float xl = (v == 0.0f) ? 0.0f : v * (fast_lg2(rate) * PPB_LN2);
     const int k = (int)v;
     const float lg = (v >= 0.0f && v < 64.0f && (float)k == v) ? tab[k] : lgammaf(v + 1.0f);
     return xl - rate - lg;
@@ -175,10 +185,6 @@ __global__ void __launch_bounds__(kThreads) k_categorical(const float* __restric
 // (truncated components: sigma_k -> sigma_k Z_k, and -inf outside [low, high]): one exp and one reciprocal per component and
 // ONE log per particle instead of two logs, an exp and two divisions per component — these kernels are bound by the
 // transcendental/ALU rate, not by HBM (ncu: profiles/).  Same value as the reference's formula up to fp32 rounding.
-__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float fast_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-
 // EXACT: K == KMAX is known at compile time (the component loops carry no k < K predicates)
 template <int KMAX, bool TRUNC, bool EXACT = false>
 __device__ __forceinline__ float mixture_row(float v, const float* __restrict__ m, const float* __restrict__ s,
