@@ -98,6 +98,8 @@ struct ppb_net {
   void* host_state_dev = nullptr;   // 16 B Adam state (ppb_adam_step_dev)
   float host_hyper[6] = {0, 0, 0, 0, 0, 0};
   int64_t host_step_dev = -1;       // value of the device step counter
+  char* host_pin = nullptr;         // pinned staging: [image bytes | 8 B loss + status]; both copies are nodes of the step graph
+  int64_t host_pin_cap = 0;
   // pinned staging ring for problem lists
   Problem* h_stage[2] = {nullptr, nullptr};
   cudaEvent_t ev_stage[2] = {nullptr, nullptr};
@@ -1160,6 +1162,7 @@ int ppb_net_destroy(ppb_net* net) {
   if (net->host_stream) cudaStreamDestroy(net->host_stream);
   if (net->host_hyper_dev) cudaFree(net->host_hyper_dev);
   if (net->host_state_dev) cudaFree(net->host_state_dev);
+  if (net->host_pin) cudaFreeHost(net->host_pin);
   delete net;
   return PPB_OK;
 }
@@ -1980,7 +1983,20 @@ int ppb_ic_train_step_host(ppb_net* net, float* arena, float* grad_arena, float*
     net->host_step_dev = 0;
   }
   cudaStream_t hs = net->host_stream;
+  // The host->device copy of the batch image and the device->host read of (loss, status) are NODES of the step graph, out of
+  // and into an internal pinned staging buffer: one cudaGraphLaunch + one synchronise per step instead of five stream calls,
+  // and the copies start without a stream round trip.
+  if (net->host_pin_cap < batch_image_bytes + 16) {
+    PPB_CUDA(cudaStreamSynchronize(hs));
+    if (net->host_pin) cudaFreeHost(net->host_pin);
+    net->host_pin_cap = 2 * batch_image_bytes + 16;
+    PPB_CUDA(cudaHostAlloc((void**)&net->host_pin, (size_t)net->host_pin_cap, cudaHostAllocDefault));
+  }
+  char* const pin_img = net->host_pin;
+  char* const pin_res = net->host_pin + (net->host_pin_cap - 16);
   uint64_t key = fnv1a(&d, sizeof(d));
+  key = fnv1a(&batch_image_bytes, sizeof(batch_image_bytes), key);
+  key = fnv1a(&pin_img, sizeof(pin_img), key);
   key = fnv1a(b.row_off_host, sizeof(int32_t) * (d.T + 1), key);
   key = fnv1a(b.group_addr_host, sizeof(int32_t) * d.G, key);
   key = fnv1a(b.group_start_host, sizeof(int32_t) * (d.G + 1), key);
@@ -2001,7 +2017,7 @@ int ppb_ic_train_step_host(ppb_net* net, float* arena, float* grad_arena, float*
   // order after whatever the caller queued on its stream
   rc = stream_after(net, st, hs);
   if (rc) return rc;
-  PPB_CUDA(cudaMemcpyAsync(batch_image_dev, batch_image_host, batch_image_bytes, cudaMemcpyHostToDevice, hs));
+  memcpy(pin_img, batch_image_host, (size_t)batch_image_bytes);
   const float hyper[6] = {lr, beta1, beta2, eps, weight_decay, 1.0f};
   if (memcmp(hyper, net->host_hyper, sizeof(hyper)) != 0) {
     memcpy(net->host_hyper, hyper, sizeof(hyper));
@@ -2013,13 +2029,17 @@ int ppb_ic_train_step_host(ppb_net* net, float* arena, float* grad_arena, float*
     PPB_CUDA(cudaStreamSynchronize(hs));   // `prev` lives on this frame
   }
   auto enqueue = [&](cudaStream_t q) -> int {
+    PPB_CUDA(cudaMemcpyAsync(batch_image_dev, pin_img, batch_image_bytes, cudaMemcpyHostToDevice, q));
     PPB_CUDA(cudaMemsetAsync(grad_arena, 0, arena_floats * sizeof(float), q));
     int r = ppb_ic_loss_forward(net, arena, &b, workspace, need, precision, loss_dev, status_dev, nullptr, 1, (void*)q);
     if (r) return r;
     r = ppb_ic_loss_backward(net, arena, grad_arena, &b, workspace, need, precision, 1.0f, (void*)q);
     if (r) return r;
-    return ppb_adam_step_dev(arena, grad_arena, exp_avg, exp_avg_sq, arena_floats, net->host_hyper_dev, net->host_state_dev,
-                             (void*)q);
+    r = ppb_adam_step_dev(arena, grad_arena, exp_avg, exp_avg_sq, arena_floats, net->host_hyper_dev, net->host_state_dev,
+                          (void*)q);
+    if (r) return r;
+    PPB_CUDA(cudaMemcpyAsync(pin_res, loss_dev, 8, cudaMemcpyDeviceToHost, q));   // loss (float) + status (int32), adjacent
+    return PPB_OK;
   };
   if (net->host_exec) {
     PPB_CUDA(cudaGraphLaunch(net->host_exec, hs));
@@ -2049,9 +2069,9 @@ int ppb_ic_train_step_host(ppb_net* net, float* arena, float* grad_arena, float*
   }
   net->host_seen += 1;
   net->host_step_dev = step;
-  if (loss_host) PPB_CUDA(cudaMemcpyAsync(loss_host, loss_dev, sizeof(float), cudaMemcpyDeviceToHost, hs));
-  if (status_host) PPB_CUDA(cudaMemcpyAsync(status_host, status_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, hs));
   PPB_CUDA(cudaStreamSynchronize(hs));
+  if (loss_host) memcpy(loss_host, pin_res, sizeof(float));
+  if (status_host) memcpy(status_host, pin_res + sizeof(float), sizeof(int32_t));
   return PPB_OK;
 }
 

@@ -7,9 +7,10 @@ TMP=$(mktemp)
 cuobjdump -sass "$LIB" > "$TMP"
 {
   echo "# cuobjdump -sass $LIB (sm_100a): instructions per mnemonic (word match), round 2"
-  for m in UTCHMMA UTCQMMA LDTM STTM UTCBAR UTCATOMSWS UBLKCP UTMALDG UTMASTG SYNCS UCGABAR_ARV UCGABAR_WAIT LDGSTS HMMA HGMMA; do
+  for m in UTCHMMA UTCQMMA LDTM STTM UTCBAR UTCATOMSWS UBLKCP UTMALDG UTMASTG SYNCS UCGABAR_ARV UCGABAR_WAIT PREEXIT ACQBULK LDGSTS HMMA HGMMA; do
     printf "%-14s %s\n" "$m" "$(grep -cE "[^A-Z]$m[. ]" "$TMP" || true)"
   done
+  echo "# PREEXIT = griddepcontrol.launch_dependents, ACQBULK = griddepcontrol.wait (programmatic dependent launch)"
   echo
   echo "# tcgen05.mma (UTCHMMA) per kernel:"
   awk '/Function :/{f=$3} /[^A-Z]UTCHMMA/{c[f]++} END{for(k in c) print c[k], k}' "$TMP" | sort -k2 | c++filt | cut -c1-140
