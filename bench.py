@@ -262,6 +262,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner (NCCL_DEBUG=VERSION prints one) goes to stderr
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
     rng = np.random.default_rng(1234 + rank)
     net = synthetic.gum_network(lstm_dim=LSTM_DIM, precision=args.precision, seed=0)

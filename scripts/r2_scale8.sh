@@ -8,7 +8,7 @@ for n in 8 4 2; do
   echo "== bench $n =="; python - <<PY
 import json
 try:
-    d = json.load(open('gpurun_out/r2_bench_${n}gpu.json'))
+    d = json.loads([l for l in open('gpurun_out/r2_bench_${n}gpu.json') if l.startswith('{')][-1])
     print(d['n_gpus'], d['value'], d['ms_per_step'], d.get('dp_step_phases_us_rank0'), d['ms_per_step_stats_rank0'], d['e2e'])
 except Exception as e:
     print('no line', e)
