@@ -1783,7 +1783,7 @@ int ppb_adam_step(float* arena, const float* grad, float* exp_avg, float* exp_av
                   float beta2, float eps, float weight_decay, int64_t step, float grad_scale, void* stream) {
   PPB_CHECK_ARG(arena && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "bad arguments");
   double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-  PPB_CUDA(ppb_launch(k_adam, dim3(ppb_grid_for(n, 256, 4)), dim3(256), 0, (cudaStream_t)stream, 2, 0, arena, grad, exp_avg,
+  PPB_CUDA(ppb_launch(k_adam, dim3(ppb_grid_for(n, 256, 4)), dim3(256), 0, (cudaStream_t)stream, 3, 0, arena, grad, exp_avg,
                       exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale));
   PPB_LAUNCH_CHECK();
   return PPB_OK;
@@ -1797,7 +1797,7 @@ int ppb_adam_step_dev(float* arena, const float* grad, float* exp_avg, float* ex
                       const float* hyper_dev, void* state_dev, void* stream) {
   PPB_CHECK_ARG(arena && grad && exp_avg && exp_avg_sq && hyper_dev && state_dev && n > 0, "bad arguments");
   const int vec = ((((uintptr_t)arena | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0) ? 1 : 0;
-  PPB_CUDA(ppb_launch(k_adam_dev, dim3(ppb_grid_for(n, 256, 4)), dim3(256), 0, (cudaStream_t)stream, 2, 0, arena, grad,
+  PPB_CUDA(ppb_launch(k_adam_dev, dim3(ppb_grid_for(n, 256, 4)), dim3(256), 0, (cudaStream_t)stream, 3, 0, arena, grad,
                       exp_avg, exp_avg_sq, n, vec, hyper_dev, (long long*)state_dev, (float*)((char*)state_dev + 8),
                       (unsigned int*)((char*)state_dev + 12)));
   PPB_LAUNCH_CHECK();

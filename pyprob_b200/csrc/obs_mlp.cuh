@@ -274,6 +274,7 @@ __device__ __forceinline__ void warp_dense_fwd(const float* in, int in_dim, cons
 
 __global__ void __launch_bounds__(kWarps * 32) k_fwd2(Net net, const float* __restrict__ arena,
                                                       const float* __restrict__ obs, int B, int traces_per_cta, Bufs bufs) {
+  ppb_pdl_trigger();   // the P_obs GEMM that follows is launched with the PDL attribute: its prologue overlaps this kernel
   extern __shared__ float smem[];
   // stage every layer once per CTA
   float* p = smem;
