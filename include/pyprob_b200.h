@@ -364,9 +364,13 @@ int ppb_net_refresh_weights(ppb_net* net, const float* arena, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 5. Host-buffer convenience entry (the end-to-end call bench.py times as `e2e`)
- *    One IC training step from an encoded batch in pinned HOST memory: H2D of the batch image,
+ *    One IC training step from an encoded batch in HOST memory: H2D of the batch image,
  *    forward, backward, Adam, D2H of the loss.  batch_image_host is the packed layout produced by
  *    pyprob_b200.encoding.pack_batch (header ints + arrays); see DESIGN.md §3.
+ *    The call returns when the step has finished (loss_host / status_host are valid).  After the first call
+ *    with a given batch STRUCTURE the whole step — including both copies, staged through an internal pinned
+ *    buffer, so batch_image_host need not be pinned — replays from one CUDA graph (PPB_HOST_STEP_GRAPH=0:
+ *    plain stream launches).
  * ---------------------------------------------------------------------------------------------- */
 int ppb_ic_train_step_host(ppb_net* net, float* arena, float* grad_arena, float* exp_avg,
                            float* exp_avg_sq, int64_t arena_floats, const void* batch_image_host,
