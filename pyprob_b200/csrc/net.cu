@@ -486,167 +486,176 @@ __global__ void __launch_bounds__(256) k_cell_fwd(float* __restrict__ gates, con
 // heads: family transform + log q(value) + d(-log q)/d out, loss reduction (:199-218).
 // One WARP per row: lane k owns mixture component k (or categories k, k+32, ...), reductions are shuffles;
 // the formulas are those of heads.cuh (mixture_nll / categorical_nll), restated lane-parallel.
-__global__ void __launch_bounds__(256) k_head_nll(const float* __restrict__ out_raw, int out_pad,
-                                                   const ppb_addr_desc* __restrict__ addrs,
-                                                   const int* __restrict__ row_step, const int* __restrict__ step_addr,
-                                                   const float* __restrict__ values, const float* __restrict__ prior0,
-                                                   const float* __restrict__ prior1, const int* __restrict__ row_trace,
-                                                   int R, int K, float inv_batch, float* __restrict__ row_lp,
-                                                   float* __restrict__ d_out, HImg dimg, float* __restrict__ loss_acc,
-                                                   float* __restrict__ loss_out, int* __restrict__ status_out) {
-  ppb_pdl_trigger();
-  ppb_pdl_wait();
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+// nll_row is the per-row routine (x = the row's raw head outputs, global or shared memory); two kernels call it:
+// k_head_nll (x read from the output of the h2 GEMM) and k_head_out_nll (x computed in the kernel, below).
+struct NllArgs {
+  const ppb_addr_desc* addrs;
+  const int* row_step; const int* step_addr;
+  const float* values; const float* prior0; const float* prior1;
+  const int* row_trace;
+  int K; float inv_batch;
+  float* row_lp; float* d_out; int out_pad;
+  HImg dimg;
+};
+__device__ __forceinline__ void nll_row(const NllArgs& A, const float* x, int row, int lane, float& local, int& bad) {
+  const ppb_addr_desc* addrs = A.addrs;
+  const int* row_step = A.row_step; const int* step_addr = A.step_addr;
+  const float* values = A.values; const float* prior0 = A.prior0; const float* prior1 = A.prior1;
+  const int* row_trace = A.row_trace;
+  const int K = A.K, out_pad = A.out_pad;
+  const float inv_batch = A.inv_batch;
+  float* row_lp = A.row_lp; float* d_out = A.d_out;
+  const HImg dimg = A.dimg;
   const int img_cols = (int)dimg.kb * 32;
-  float local = 0.0f;
-  int bad = 0;
-  for (int row = warp; row < R; row += nwarps) {
-    const bool valid = row_trace[row] >= 0;
-    float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;  // this lane's gradient entries (mixture: m,s,p ; categorical: 4 cats)
-    float lp = 0.0f;
-    int O = 0;
-    bool is_cat = false;
-    if (valid) {
-      const ppb_addr_desc a = addrs[step_addr[row_step[row]]];
-      const float* x = out_raw + (int64_t)row * out_pad;
-      const float v = values[row];
-      O = a.head_out;
-      is_cat = a.family == PPB_FAMILY_CATEGORICAL;
-      if (is_cat) {
-        const int C = a.num_categories;
-        float q[4], xs[4];
-        float mx = -INFINITY;
+  const bool valid = row_trace[row] >= 0;
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;  // this lane's gradient entries (mixture: m,s,p ; categorical: 4 cats)
+  float lp = 0.0f;
+  int O = 0;
+  bool is_cat = false;
+  if (valid) {
+    const ppb_addr_desc a = addrs[step_addr[row_step[row]]];
+    const float v = values[row];
+    O = a.head_out;
+    is_cat = a.family == PPB_FAMILY_CATEGORICAL;
+    if (is_cat) {
+      const int C = a.num_categories;
+      float q[4], xs[4];
+      float mx = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { int c = lane + 32 * i; xs[i] = c < C ? x[c] : -INFINITY; mx = fmaxf(mx, xs[i]); }
-        mx = ppb_warp_max(mx);
-        float s = 0.0f;
+      for (int i = 0; i < 4; ++i) { int c = lane + 32 * i; xs[i] = c < C ? x[c] : -INFINITY; mx = fmaxf(mx, xs[i]); }
+      mx = ppb_warp_max(mx);
+      float s = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { q[i] = (lane + 32 * i < C) ? expf(xs[i] - mx) : 0.0f; s += q[i]; }
-        s = ppb_warp_sum(s);
-        float S = 0.0f;
+      for (int i = 0; i < 4; ++i) { q[i] = (lane + 32 * i < C) ? expf(xs[i] - mx) : 0.0f; s += q[i]; }
+      s = ppb_warp_sum(s);
+      float S = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { q[i] = (lane + 32 * i < C) ? q[i] / s + PPB_UTIL_EPSILON : 0.0f; S += q[i]; }
-        S = ppb_warp_sum(S);
-        const int iv = (int)v;
-        if (iv < 0 || iv >= C) {
-          lp = NAN;
-        } else {
-          float qv = 0.0f;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) if (lane + 32 * i == iv) qv = q[i];
-          qv = ppb_warp_sum(qv);
-          float ph = qv / S;
-          bool clamped = (ph < PPB_EPS32) || (ph > 1.0f - PPB_EPS32);
-          lp = logf(ppb_clamp_prob(ph));
-          if (!clamped && lp > -INFINITY) {
-            float dot = 0.0f, g[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              int c = lane + 32 * i;
-              g[i] = c < C ? ((c == iv) ? 1.0f / qv : 0.0f) - 1.0f / S : 0.0f;
-              dot += c < C ? (q[i] - PPB_UTIL_EPSILON) * g[i] : 0.0f;
-            }
-            dot = ppb_warp_sum(dot);
-            g0 = -((q[0] - PPB_UTIL_EPSILON) * (g[0] - dot));
-            g1 = (lane + 32 < C) ? -((q[1] - PPB_UTIL_EPSILON) * (g[1] - dot)) : 0.f;
-            g2 = (lane + 64 < C) ? -((q[2] - PPB_UTIL_EPSILON) * (g[2] - dot)) : 0.f;
-            g3 = (lane + 96 < C) ? -((q[3] - PPB_UTIL_EPSILON) * (g[3] - dot)) : 0.f;
-            if (lane >= C) g0 = 0.f;
-          }
-        }
+      for (int i = 0; i < 4; ++i) { q[i] = (lane + 32 * i < C) ? q[i] / s + PPB_UTIL_EPSILON : 0.0f; S += q[i]; }
+      S = ppb_warp_sum(S);
+      const int iv = (int)v;
+      if (iv < 0 || iv >= C) {
+        lp = NAN;
       } else {
-        const bool on = lane < K;
-        const int fam = a.family;
-        const float p0 = prior0[row], p1 = prior1[row];
-        const float xm = on ? x[lane] : 0.f, xsd = on ? x[K + lane] : 0.f, xp = on ? x[2 * K + lane] : -INFINITY;
-        float mx = ppb_warp_max(xp);
-        float e = on ? expf(xp - mx) : 0.0f;
-        float prob = e / ppb_warp_sum(e);
-        float mean, sd, lo = 0.f, hi = 0.f;
-        if (fam == PPB_FAMILY_NORMAL) { mean = p0 + xm * p1; sd = expf(xsd) * p1; }
-        else if (fam == PPB_FAMILY_UNIFORM) {
-          float range = p1 - p0;
-          mean = p0 + heads::sigmoidf_(xm) * range;
-          sd = range / 1000.0f + heads::sigmoidf_(xsd) * range * 10.0f;
-          lo = p0; hi = p1;
-        } else { mean = heads::sigmoidf_(xm) * 40.0f; sd = expf(xsd); lo = 0.f; hi = 40.f; }
-        const bool trunc = fam != PPB_FAMILY_NORMAL;
-        float S = ppb_warp_sum(on ? prob : 0.0f);
-        float ph = prob / S;
+        float qv = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (lane + 32 * i == iv) qv = q[i];
+        qv = ppb_warp_sum(qv);
+        float ph = qv / S;
         bool clamped = (ph < PPB_EPS32) || (ph > 1.0f - PPB_EPS32);
-        float lw = logf(ppb_clamp_prob(ph));
-        float lpk = trunc ? ppb_truncnormal_lp(v, mean, sd, lo, hi) : ppb_normal_lp(v, mean, sd);
-        float t = on ? lw + lpk : -INFINITY;
-        if (on && isnan(t)) t = NAN;
-        float mxt = ppb_warp_max(t);
-        // NaN anywhere poisons the row (reference: has_nan_or_inf on the log_prob)
-        bool any_nan = __any_sync(0xffffffffu, on && isnan(t));
-        if (any_nan) lp = NAN;
-        else if (mxt == -INFINITY) lp = -INFINITY;
-        else lp = mxt + logf(ppb_warp_sum(on ? expf(t - mxt) : 0.0f));
-        if (lp > -INFINITY && lp < INFINITY) {
-          float r = on ? expf(t - lp) : 0.0f;
-          float sum_r_unc = ppb_warp_sum((on && !clamped) ? r : 0.0f);
-          float direct = (on && !clamped) ? r / ph : 0.0f;
-          float g_prob = (direct - sum_r_unc) / S;
-          float dot = ppb_warp_sum(on ? prob * g_prob : 0.0f);
-          float z = (v - mean) / sd, dmu, dsd;
-          if (!trunc) { dmu = z / sd; dsd = (z * z - 1.0f) / sd; }
-          else {
-            float alpha = (lo - mean) / sd, beta = (hi - mean) / sd;
-            float Z = ppb_std_normal_cdf(beta) - ppb_std_normal_cdf(alpha);
-            float pa = heads::std_normal_pdf(alpha), pb = heads::std_normal_pdf(beta);
-            dmu = z / sd - (pa - pb) / (sd * Z);
-            dsd = (z * z - 1.0f) / sd - (alpha * pa - beta * pb) / (sd * Z);
+        lp = logf(ppb_clamp_prob(ph));
+        if (!clamped && lp > -INFINITY) {
+          float dot = 0.0f, g[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            int c = lane + 32 * i;
+            g[i] = c < C ? ((c == iv) ? 1.0f / qv : 0.0f) - 1.0f / S : 0.0f;
+            dot += c < C ? (q[i] - PPB_UTIL_EPSILON) * g[i] : 0.0f;
           }
-          dmu *= r; dsd *= r;
-          float dxm, dxs;
-          if (fam == PPB_FAMILY_NORMAL) { dxm = dmu * p1; dxs = dsd * sd; }
-          else if (fam == PPB_FAMILY_UNIFORM) {
-            float range = p1 - p0, sm = heads::sigmoidf_(xm), ss = heads::sigmoidf_(xsd);
-            dxm = dmu * sm * (1.0f - sm) * range;
-            dxs = dsd * ss * (1.0f - ss) * range * 10.0f;
-          } else { float sm = heads::sigmoidf_(xm); dxm = dmu * sm * (1.0f - sm) * 40.0f; dxs = dsd * sd; }
-          if (on) { g0 = -dxm; g1 = -dxs; g2 = -(prob * (g_prob - dot)); }
+          dot = ppb_warp_sum(dot);
+          g0 = -((q[0] - PPB_UTIL_EPSILON) * (g[0] - dot));
+          g1 = (lane + 32 < C) ? -((q[1] - PPB_UTIL_EPSILON) * (g[1] - dot)) : 0.f;
+          g2 = (lane + 64 < C) ? -((q[2] - PPB_UTIL_EPSILON) * (g[2] - dot)) : 0.f;
+          g3 = (lane + 96 < C) ? -((q[3] - PPB_UTIL_EPSILON) * (g[3] - dot)) : 0.f;
+          if (lane >= C) g0 = 0.f;
         }
       }
-      if (lp == -INFINITY) { lp = PPB_LOG_EPSILON; g0 = g1 = g2 = g3 = 0.f; }  // util.replace_negative_inf (:213)
-      if (isnan(lp) || isinf(lp)) { if (lane == 0) bad += 1; lp = 0.0f; g0 = g1 = g2 = g3 = 0.f; }
-      if (lane == 0) local += -lp;
-    }
-    if (row_lp && lane == 0) row_lp[row] = lp;
-    // scatter this lane's entries; everything else in the (padded) row is zero
-    if (d_out) {
-      const int ncols = (dimg.k_hi && img_cols > out_pad) ? img_cols : out_pad;
-      auto put = [&](int j, float gv) {
-        gv *= inv_batch;
-        if (j < out_pad) d_out[(int64_t)row * out_pad + j] = gv;
-        if (dimg.k_hi && j < img_cols) tcg::img_store(dimg.k_hi, dimg.k_lo, dimg.mn_hi, dimg.mn_lo, row, j, dimg.kb, gv);
-      };
-      if (valid) {
-        if (is_cat) {
-          if (lane < O) put(lane, g0);
-          if (lane + 32 < O) put(lane + 32, g1);
-          if (lane + 64 < O) put(lane + 64, g2);
-          if (lane + 96 < O) put(lane + 96, g3);
-        } else if (lane < K) {
-          put(lane, g0); put(K + lane, g1); put(2 * K + lane, g2);
+    } else {
+      const bool on = lane < K;
+      const int fam = a.family;
+      const float p0 = prior0[row], p1 = prior1[row];
+      const float xm = on ? x[lane] : 0.f, xsd = on ? x[K + lane] : 0.f, xp = on ? x[2 * K + lane] : -INFINITY;
+      float mx = ppb_warp_max(xp);
+      float e = on ? expf(xp - mx) : 0.0f;
+      float prob = e / ppb_warp_sum(e);
+      float mean, sd, lo = 0.f, hi = 0.f;
+      if (fam == PPB_FAMILY_NORMAL) { mean = p0 + xm * p1; sd = expf(xsd) * p1; }
+      else if (fam == PPB_FAMILY_UNIFORM) {
+        float range = p1 - p0;
+        mean = p0 + heads::sigmoidf_(xm) * range;
+        sd = range / 1000.0f + heads::sigmoidf_(xsd) * range * 10.0f;
+        lo = p0; hi = p1;
+      } else { mean = heads::sigmoidf_(xm) * 40.0f; sd = expf(xsd); lo = 0.f; hi = 40.f; }
+      const bool trunc = fam != PPB_FAMILY_NORMAL;
+      float S = ppb_warp_sum(on ? prob : 0.0f);
+      float ph = prob / S;
+      bool clamped = (ph < PPB_EPS32) || (ph > 1.0f - PPB_EPS32);
+      float lw = logf(ppb_clamp_prob(ph));
+      float lpk = trunc ? ppb_truncnormal_lp(v, mean, sd, lo, hi) : ppb_normal_lp(v, mean, sd);
+      float t = on ? lw + lpk : -INFINITY;
+      if (on && isnan(t)) t = NAN;
+      float mxt = ppb_warp_max(t);
+      // NaN anywhere poisons the row (reference: has_nan_or_inf on the log_prob)
+      bool any_nan = __any_sync(0xffffffffu, on && isnan(t));
+      if (any_nan) lp = NAN;
+      else if (mxt == -INFINITY) lp = -INFINITY;
+      else lp = mxt + logf(ppb_warp_sum(on ? expf(t - mxt) : 0.0f));
+      if (lp > -INFINITY && lp < INFINITY) {
+        float r = on ? expf(t - lp) : 0.0f;
+        float sum_r_unc = ppb_warp_sum((on && !clamped) ? r : 0.0f);
+        float direct = (on && !clamped) ? r / ph : 0.0f;
+        float g_prob = (direct - sum_r_unc) / S;
+        float dot = ppb_warp_sum(on ? prob * g_prob : 0.0f);
+        float z = (v - mean) / sd, dmu, dsd;
+        if (!trunc) { dmu = z / sd; dsd = (z * z - 1.0f) / sd; }
+        else {
+          float alpha = (lo - mean) / sd, beta = (hi - mean) / sd;
+          float Z = ppb_std_normal_cdf(beta) - ppb_std_normal_cdf(alpha);
+          float pa = heads::std_normal_pdf(alpha), pb = heads::std_normal_pdf(beta);
+          dmu = z / sd - (pa - pb) / (sd * Z);
+          dsd = (z * z - 1.0f) / sd - (alpha * pa - beta * pb) / (sd * Z);
         }
+        dmu *= r; dsd *= r;
+        float dxm, dxs;
+        if (fam == PPB_FAMILY_NORMAL) { dxm = dmu * p1; dxs = dsd * sd; }
+        else if (fam == PPB_FAMILY_UNIFORM) {
+          float range = p1 - p0, sm = heads::sigmoidf_(xm), ss = heads::sigmoidf_(xsd);
+          dxm = dmu * sm * (1.0f - sm) * range;
+          dxs = dsd * ss * (1.0f - ss) * range * 10.0f;
+        } else { float sm = heads::sigmoidf_(xm); dxm = dmu * sm * (1.0f - sm) * 40.0f; dxs = dsd * sd; }
+        if (on) { g0 = -dxm; g1 = -dxs; g2 = -(prob * (g_prob - dot)); }
       }
-      for (int j = (valid ? O : 0) + lane; j < ncols; j += 32) put(j, 0.0f);
     }
+    if (lp == -INFINITY) { lp = PPB_LOG_EPSILON; g0 = g1 = g2 = g3 = 0.f; }  // util.replace_negative_inf (:213)
+    if (isnan(lp) || isinf(lp)) { if (lane == 0) bad += 1; lp = 0.0f; g0 = g1 = g2 = g3 = 0.f; }
+    if (lane == 0) local += -lp;
   }
+  if (row_lp && lane == 0) row_lp[row] = lp;
+  // scatter this lane's entries; everything else in the (padded) row is zero
+  if (d_out) {
+    const int ncols = (dimg.k_hi && img_cols > out_pad) ? img_cols : out_pad;
+    auto put = [&](int j, float gv) {
+      gv *= inv_batch;
+      if (j < out_pad) d_out[(int64_t)row * out_pad + j] = gv;
+      if (dimg.k_hi && j < img_cols) tcg::img_store(dimg.k_hi, dimg.k_lo, dimg.mn_hi, dimg.mn_lo, row, j, dimg.kb, gv);
+    };
+    if (valid) {
+      if (is_cat) {
+        if (lane < O) put(lane, g0);
+        if (lane + 32 < O) put(lane + 32, g1);
+        if (lane + 64 < O) put(lane + 64, g2);
+        if (lane + 96 < O) put(lane + 96, g3);
+      } else if (lane < K) {
+        put(lane, g0); put(K + lane, g1); put(2 * K + lane, g2);
+      }
+    }
+    for (int j = (valid ? O : 0) + lane; j < ncols; j += 32) put(j, 0.0f);
+  }
+  }
+
+// sum of -log q and count of failed rows -> loss accumulators; the last block to finish publishes the totals
+// (loss_acc[2] counts finished blocks; zeroed with the accumulators)
+__device__ __forceinline__ void nll_finish(float local, int bad, int lane, float inv_batch, unsigned int n_blocks,
+                                           float* __restrict__ loss_acc, float* __restrict__ loss_out,
+                                           int* __restrict__ status_out) {
   if (lane == 0) {
     if (local != 0.0f) atomicAdd(loss_acc, local * inv_batch);
     if (bad) atomicAdd(reinterpret_cast<int*>(loss_acc + 1), bad);
   }
-  // the last block to finish publishes the totals (loss_acc[2] counts finished blocks; zeroed with the accumulators)
   __shared__ int s_last;
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    s_last = atomicAdd(reinterpret_cast<unsigned int*>(loss_acc + 2), 1u) == gridDim.x - 1;
+    s_last = atomicAdd(reinterpret_cast<unsigned int*>(loss_acc + 2), 1u) == n_blocks - 1;
   }
   __syncthreads();
   if (s_last && threadIdx.x == 0) {
@@ -654,6 +663,104 @@ __global__ void __launch_bounds__(256) k_head_nll(const float* __restrict__ out_
     if (loss_out) *loss_out = atomicAdd(loss_acc, 0.0f);
     if (status_out) *status_out = atomicAdd(reinterpret_cast<int*>(loss_acc + 1), 0);
   }
+}
+
+__global__ void __launch_bounds__(256) k_head_nll(const float* __restrict__ out_raw, NllArgs A, int R,
+                                                   float* __restrict__ loss_acc, float* __restrict__ loss_out,
+                                                   int* __restrict__ status_out) {
+  ppb_pdl_trigger();
+  ppb_pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  float local = 0.0f;
+  int bad = 0;
+  for (int row = warp; row < R; row += nwarps) nll_row(A, out_raw + (int64_t)row * A.out_pad, row, lane, local, bad);
+  nll_finish(local, bad, lane, A.inv_batch, gridDim.x, loss_acc, loss_out, status_out);
+}
+
+// The output layer of the proposal heads and the NLL in ONE kernel, on the CUDA cores.  The layer is tiny (hidden <= ~300,
+// out = 3K or C <= 128: 8 k MACs per row at configs[1]) but as a tensor-core launch it is a padded 128-wide tile in 3xTF32 plus
+// a kernel boundary: 9.3 us + 7.4 us + a 2 us gap on the configs[1] chain, 62 us at T = 50.  Here blockIdx.y = segment
+// (rows that share an address, hence W2), a block stages that address's W2 and b2 in shared memory once — BEFORE the PDL
+// wait: the weights are not written inside a training step — and each warp walks its rows: hidden activations = hi + lo of the
+// K-format tile image the h1 GEMM wrote (the same two words the tensor-core path multiplies), 4-way split dot products,
+// then nll_row on the outputs in shared memory.
+__global__ void __launch_bounds__(256) k_head_out_nll(const float* __restrict__ arena, const float* __restrict__ hid_hi,
+                                                       const float* __restrict__ hid_lo, int64_t hid_kb,
+                                                       const int* __restrict__ step_row0, const int* __restrict__ step_nrows,
+                                                       int rows_per_block, NllArgs A, float* __restrict__ out_raw,
+                                                       float* __restrict__ loss_acc, float* __restrict__ loss_out,
+                                                       int* __restrict__ status_out) {
+  ppb_pdl_trigger();
+  extern __shared__ float sm_head[];
+  const int seg = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const ppb_addr_desc a = A.addrs[A.step_addr[seg]];
+  // rows of W2 at a pitch of 4 x (odd) floats: 16-byte shared-memory loads whose quarter-warps hit eight different bank groups
+  const int Hh = a.head_hidden, O = a.head_out, Hh4 = (Hh + 3) & ~3;
+  const int pitch = ((Hh4 >> 2) & 1) ? Hh4 : Hh4 + 4;
+  float* w2s = sm_head;                       // [O][pitch], columns >= Hh zero
+  float* b2s = w2s + (size_t)O * pitch;       // [O]
+  float* hrow = b2s + ((O + 3) & ~3) + (size_t)warp * (Hh4 + 128);   // per warp: hidden row (zero-padded to Hh4), 128 outputs
+  float* xout = hrow + Hh4;
+  const int r0 = step_row0[seg] + blockIdx.x * rows_per_block;
+  int r1 = r0 + rows_per_block;
+  // the padding rows of the segment (up to the next multiple of 128) are walked too: nll_row zero-fills their gradient rows
+  // and images, which the weight-gradient reductions read
+  const int seg_end = step_row0[seg] + step_nrows[seg];
+  const int seg_end_pad = step_row0[seg] + ((step_nrows[seg] + 127) & ~127);
+  if (r1 > seg_end_pad) r1 = seg_end_pad;
+  const bool any = r0 < r1 && r0 < seg_end;
+  if (any) {
+    const float* w2 = arena + a.w2_off;
+    for (int i = threadIdx.x; i < O * pitch; i += blockDim.x) {
+      const int o = i / pitch, k = i - o * pitch;
+      w2s[i] = (k < Hh) ? __ldg(w2 + (int64_t)o * Hh + k) : 0.0f;
+    }
+    for (int o = threadIdx.x; o < O; o += blockDim.x) b2s[o] = __ldg(arena + a.b2_off + o);
+  }
+  ppb_pdl_wait();
+  __syncthreads();
+  float local = 0.0f;
+  int bad = 0;
+  for (int row = r0 + warp; row < r1; row += 8) {
+    if (row >= seg_end) {   // warp-uniform: padding row
+      nll_row(A, xout, row, lane, local, bad);
+      continue;
+    }
+    // hidden activations of the row: hi + lo of the K-format image (32 consecutive k = one swizzled 128-byte span)
+    for (int k = lane; k < Hh4; k += 32) {
+      float v = 0.0f;
+      if (k < Hh) {
+        const int64_t off = tc::packed_offset(row, k, hid_kb);
+        v = __ldg(hid_hi + off) + (hid_lo ? __ldg(hid_lo + off) : 0.0f);
+      }
+      hrow[k] = v;
+    }
+    __syncwarp();
+    for (int o0 = 0; o0 < O; o0 += 32) {
+      const int o = o0 + lane;
+      const float4* wr = reinterpret_cast<const float4*>(w2s + (size_t)(o < O ? o : 0) * pitch);
+      const float4* hr = reinterpret_cast<const float4*>(hrow);
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+      for (int k4 = 0; k4 < (Hh4 >> 2); ++k4) {
+        const float4 h4 = hr[k4], w4 = wr[k4];
+        acc[0] = fmaf(h4.x, w4.x, acc[0]);
+        acc[1] = fmaf(h4.y, w4.y, acc[1]);
+        acc[2] = fmaf(h4.z, w4.z, acc[2]);
+        acc[3] = fmaf(h4.w, w4.w, acc[3]);
+      }
+      if (o < O) {
+        const float y = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + b2s[o];
+        xout[o] = y;
+        if (out_raw) out_raw[(int64_t)row * A.out_pad + o] = y;
+      }
+    }
+    __syncwarp();
+    nll_row(A, xout, row, lane, local, bad);
+    __syncwarp();
+  }
+  nll_finish(local, bad, lane, A.inv_batch, gridDim.x * gridDim.y, loss_acc, loss_out, status_out);
 }
 
 // LSTM cell backward, one time step (reverse order).  dgates rows of this step are produced here;
@@ -1255,10 +1362,15 @@ int ppb_ic_loss_forward(ppb_net* net, const float* arena, const ppb_batch* b, vo
   }
   rc = run_phase(bl.phases[ph_h1], w.problems, st); if (rc) return rc;
   rc = run_phase(bl.phases[ph_h2], w.problems, st); if (rc) return rc;
-  k_head_nll<<<ew_grid((int64_t)d.R * 32, 256), 256, 0, st>>>(w.out_raw, net->out_pad, net->d_addrs, b->row_step, b->step_addr,
-                                                b->values, b->prior0, b->prior1, b->row_trace, d.R, D.mixture_k,
-                                                1.0f / (float)d.B, row_lp_out ? row_lp_out : w.row_lp,
-                                                want_grad ? w.d_out : nullptr, HImg(), w.loss_acc, loss_out, status_out);
+  {
+    NllArgs na;
+    na.addrs = net->d_addrs; na.row_step = b->row_step; na.step_addr = b->step_addr;
+    na.values = b->values; na.prior0 = b->prior0; na.prior1 = b->prior1; na.row_trace = b->row_trace;
+    na.K = D.mixture_k; na.inv_batch = 1.0f / (float)d.B;
+    na.row_lp = row_lp_out ? row_lp_out : w.row_lp; na.d_out = want_grad ? w.d_out : nullptr; na.out_pad = net->out_pad;
+    na.dimg = HImg();
+    k_head_nll<<<ew_grid((int64_t)d.R * 32, 256), 256, 0, st>>>(w.out_raw, na, d.R, w.loss_acc, loss_out, status_out);
+  }
   PPB_LAUNCH_CHECK();
   return PPB_OK;
 }
