@@ -107,6 +107,25 @@ class Marsaglia(Model):
         return mu
 
 
+def test_long_traces_t400_loss_and_all_grads_vs_oracle(cuda):
+    """Trace lengths of the configs[4] kind (hundreds of LSTM steps; addresses revisited as in a simulator loop): 400 dependent
+    fused LSTM steps forward, 399 BPTT steps back, two row tiles with padding rows, a second sub-batch that ends early.
+    Tolerance 3e-4 instead of 1e-4: both sides are fp32 with different summation orders and the rounding of a 400-step
+    recurrence accumulates on both (first hardware run: loss to 1e-6, worst gradient 1.03e-4 of its tensor's maximum; the
+    50-step configs[3] shape sits at 1.6e-5)."""
+    table = [('l_n0', 'Normal', 0), ('l_c0', 'Categorical', 4), ('l_u0', 'Uniform', 0), ('l_n1', 'Normal', 0),
+             ('l_p0', 'Poisson', 0), ('l_c1', 'Categorical', 3), ('l_n2', 'Normal', 0), ('l_u1', 'Uniform', 0)]
+    rng = np.random.default_rng(17)
+    net = synthetic.build_network({'o0': {'dim': 16, 'depth': 2}}, [2], table, lstm_dim=64, mixture_components=4, seed=17,
+                                  precision=0)
+    seq_long = [int(i) for i in rng.integers(0, len(table), 400)]
+    seq_short = seq_long[:37]
+    subs = [synthetic.random_sub_batch(rng, [table[i] for i in seq_long], 130, 2),
+            synthetic.random_sub_batch(rng, [table[i] for i in seq_short], 9, 2)]
+    loss, err = _check(net, synthetic.ArrayBatch(subs), ['o0'], [2], 4, rtol=3e-4)
+    print('T = 400: loss {:.6f}, worst gradient error {:.2e} of the tensor maximum'.format(loss, err))
+
+
 def test_config3_marsaglia_ic_log_weights_vs_oracle_on_identical_values(cuda):
     pyprob.seed(21)
     pyprob.set_verbosity(0)
