@@ -19,6 +19,7 @@
 #include "tc_grouped.cuh"
 #include "tc_lstm.cuh"
 #include "tc_cluster.cuh"
+#include "tc_persist.cuh"
 #include "obs_mlp.cuh"
 
 using gemm::Problem;

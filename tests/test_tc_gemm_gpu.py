@@ -44,10 +44,12 @@ def test_pack_layout_and_split(cuda):
     assert hi[mask].abs().sum().item() == 0 and lo[mask].abs().sum().item() == 0
 
 
+@pytest.mark.parametrize('persistent', ['0', '1'])   # PPB_PERSISTENT: one CTA per SM walking the tiles (tc_persist.cuh)
 @pytest.mark.parametrize('M,N,K', [(128, 128, 32), (128, 128, 64), (256, 256, 128), (100, 70, 50), (300, 2048, 724),
-                                   (1024, 512, 512)])
+                                   (1024, 512, 512), (2000, 1500, 96), (4096, 2048, 512), (1300, 1300, 40)])
 @pytest.mark.parametrize('precision', [0, 1])
-def test_gemm_packed(cuda, M, N, K, precision):
+def test_gemm_packed(cuda, monkeypatch, M, N, K, precision, persistent):
+    monkeypatch.setenv('PPB_PERSISTENT', persistent)
     gen = torch.Generator().manual_seed(M * 7 + N * 3 + K)
     a = torch.randn(M, K, generator=gen)
     b = torch.randn(N, K, generator=gen)
