@@ -47,7 +47,8 @@ def workload_config(n_gpus):
     """What is computed — identical on the b200 arm and on the reference arm for the same --gpus."""
     return {'workload': WORKLOAD, 'global_batch': BATCH * n_gpus, 'batch_per_gpu': BATCH, 'lstm_dim': LSTM_DIM,
             'trace_length': 1, 'observe_embeddings': 'obs0:32,obs1:32 (feed-forward, depth 2)', 'mixture_components': 10,
-            'parameters': GUM_PARAMETERS, 'optimizer': 'Adam lr 1e-3', 'arithmetic': 'fp32 results (1e-4 of the reference)'}
+            'parameters': GUM_PARAMETERS, 'optimizer': 'Adam lr 1e-3', 'arithmetic': 'fp32 results (1e-4 of the reference)',
+            'l2': 'GPU arm: L2 flushed between timed steps (256 MiB memset outside the timed spans); CPU arm: not applicable'}
 
 
 def percentile_stats(ms):
