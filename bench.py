@@ -263,7 +263,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner (NCCL_DEBUG=VERSION prints one) goes to stderr
+        # keep NCCL's debug log (if NCCL_DEBUG asks for one) off stdout; the JSON line is the LAST line of stdout either way
+        # (the one-line version banner of NCCL_DEBUG=VERSION is printed before it)
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
     rng = np.random.default_rng(1234 + rank)
